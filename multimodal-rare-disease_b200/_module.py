@@ -1,0 +1,61 @@
+"""Shared base of the drop-in modules: lazily owns one Engine per device and keeps its packed
+weights in step with the module's parameters."""
+
+from __future__ import annotations
+
+from typing import Dict, Iterator, Tuple
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine
+
+
+class B200Module(nn.Module):
+    # local prefix in this module's parameter tree -> canonical prefix the library expects
+    _mrd_groups: Dict[str, str] = {}
+
+    def _mrd_options(self) -> Dict[str, float]:
+        return {}
+
+    def _mrd_named(self) -> Iterator[Tuple[str, torch.Tensor]]:
+        for local, canon in self._mrd_groups.items():
+            sub = self.get_submodule(local.rstrip(".")) if local else self
+            for n, p in sub.named_parameters():
+                yield canon + n, p
+            for n, b in sub.named_buffers():
+                yield canon + n, b
+
+    def _mrd_device(self) -> torch.device:
+        try:
+            return next(self.parameters()).device
+        except StopIteration:
+            return torch.device("cpu")
+
+    def _engine(self) -> Engine:
+        """The engine for the device the parameters live on, with up-to-date packed weights."""
+        if self.training:
+            raise NotImplementedError(
+                "the B200 path implements the inference forward (eval mode) only; call .eval() first. "
+                "The training step (dropout, batch-statistics BatchNorm, backward) is scheduled next "
+                "(SURVEY.md section 8(f)) and deliberately has no silent PyTorch fallback.")
+        dev = self._mrd_device()
+        eng = self.__dict__.get("_mrd_engine")
+        if eng is None or eng.device != dev:
+            eng = Engine(dev, self._mrd_options())
+            self.__dict__["_mrd_engine"] = eng
+        eng.sync_weights(self._mrd_named())
+        return eng
+
+    def configure_b200(self, img_chunk: int = 0, seq_chunk_tokens: int = 0) -> None:
+        """Micro-batch sizes of the engine (images per ResNet pass, tokens per BERT pass)."""
+        training, self.training = self.training, False
+        try:
+            self._engine().configure(img_chunk, seq_chunk_tokens)
+        finally:
+            self.training = training
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_mrd_engine", None)
+        return d

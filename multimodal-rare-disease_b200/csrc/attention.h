@@ -1,0 +1,16 @@
+// K3: fused masked-softmax self-attention for BERT (S <= 512, head dim 64).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace mrd {
+
+// qkv: [B*S, 3*heads*64] bf16 (columns [Q | K | V], Q pre-scaled by 1/sqrt(64));
+// mask_bias: [B,S] fp32 additive key bias (0 / -inf) or null; out: [B*S, heads*64] bf16.
+// Replaces BertSelfAttention's SDPA call (HF:models/bert/modeling_bert.py:168-207,
+// HF:integrations/sdpa_attention.py:92) without materialising the [B,1,S,S] mask.
+int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int heads,
+                      __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace mrd

@@ -1,0 +1,588 @@
+// K1/K2: persistent, warp-specialised tcgen05 implicit-GEMM kernel for sm_100a.
+//
+//   warp 0      TMA producer  : A boxes from a 4-D/5-D view of the NHWC activation (one box per
+//                               (tap, 64-channel chunk)), B boxes from the [Cout][K] weight matrix
+//   warp 1      MMA issuer    : tcgen05.mma (128 x BLOCK_N x 16, bf16 -> fp32) into a double-buffered
+//                               TMEM accumulator; also owns the TMEM allocation
+//   warps 2..5  epilogue      : tcgen05.ld -> +bias (+residual) -> ReLU/GELU -> bf16 -> swizzled smem
+//                               -> TMA store (clipped by the tensor map), optional fp32 side output
+//
+// The epilogue of tile i overlaps the main loop of tile i+1 (two accumulator stages in TMEM).
+// Reference ops replaced: torchvision Bottleneck conv+bn+relu(+add) (TV:models/resnet.py:143-163),
+// ResNet stem (TV:models/resnet.py:268-270), nn.Linear in BertSelfAttention/BertSelfOutput/
+// BertIntermediate/BertOutput (HF:models/bert/modeling_bert.py:177-179,295,340,353), and the
+// Linear layers of src/cnn_encoder.py:46-51, src/fusion_model.py:108-111,212-240,
+// src/multimodal_classifier.py:44-58.
+
+#include "gemm_conv.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace mrd {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 192;
+constexpr int kStageBufBytes = 128 * 128;  // one 128-row x 64-column bf16 store sub-tile
+constexpr int kSmemLimit = 232448;         // 227 KB opt-in limit per CTA
+
+template <int BLOCK_N, bool STEM>
+struct Cfg {
+    static constexpr int BLOCK_K = STEM ? 32 : 64;
+    static constexpr int ROW_BYTES = BLOCK_K * 2;
+    static constexpr int A_STAGE = kBlockM * ROW_BYTES;
+    static constexpr int B_STAGE = BLOCK_N * ROW_BYTES;
+    static constexpr int FIXED = 2 * kStageBufBytes + BLOCK_N * 4 + 256 + 1024;  // staging+bias+bars+align
+    static constexpr int MAX_STAGES = (kSmemLimit - FIXED) / (A_STAGE + B_STAGE);
+    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static constexpr int SMEM_BYTES = FIXED + STAGES * (A_STAGE + B_STAGE);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
+    static constexpr uint32_t LAYOUT = STEM ? 4u : 2u;  // SWIZZLE_64B : SWIZZLE_128B
+    static constexpr uint32_t SBO = 8 * ROW_BYTES;      // 8-row core-matrix group pitch
+};
+
+struct TileCoord {
+    int n_idx, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int tile) {
+    TileCoord t;
+    int m_idx = tile / p.n_tiles_n;
+    t.n_idx = tile - m_idx * p.n_tiles_n;
+    int tw_i = m_idx % p.tiles_w;
+    int r = m_idx / p.tiles_w;
+    int th_i = r % p.tiles_h;
+    int img_i = r / p.tiles_h;
+    t.w0 = tw_i * p.tw;
+    t.h0 = th_i * p.th;
+    t.n0 = img_i * p.nb;
+    return t;
+}
+
+template <int BLOCK_N, bool STEM>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using C = Cfg<BLOCK_N, STEM>;
+    constexpr int STAGES = C::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t a_smem = smem_base;
+    const uint32_t b_smem = a_smem + STAGES * C::A_STAGE;
+    const uint32_t st_smem = b_smem + STAGES * C::B_STAGE;  // 2 x 16 KB store staging (1024-aligned)
+    const uint32_t bias_smem = st_smem + 2 * kStageBufBytes;
+    const uint32_t bar_smem = bias_smem + BLOCK_N * 4;
+    float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_smem - smem_base));
+    uint8_t* st_gen = smem_gen + (st_smem - smem_base);
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_smem - smem_base) + 192);
+
+    auto full_bar = [&](int s) { return bar_smem + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_smem + 64u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_smem + 128u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_smem + 144u + 8u * a; };
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.c_map);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 192);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_k = p.num_taps * p.kc_per_tap;
+    const uint32_t a_box_bytes = static_cast<uint32_t>(p.tw * p.th * p.nb) * C::ROW_BYTES;
+    const uint32_t stage_tx = a_box_bytes + C::B_STAGE;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(full_bar(stage), stage_tx);
+                    const uint32_t a_dst = a_smem + stage * C::A_STAGE;
+                    const uint32_t b_dst = b_smem + stage * C::B_STAGE;
+                    if constexpr (STEM) {
+                        tma_load_5d(&p.a_map[0], full_bar(stage), a_dst, 0, t.w0, t.h0, ks, t.n0);
+                    } else {
+                        const int tap = ks / p.kc_per_tap;
+                        const int kc = ks - tap * p.kc_per_tap;
+                        const TapDesc td = p.taps[tap];
+                        tma_load_4d(&p.a_map[td.map], full_bar(stage), a_dst, kc * C::BLOCK_K,
+                                    t.w0 + td.dw, t.h0 + td.dh, t.n0);
+                    }
+                    tma_load_2d(&p.b_map, full_bar(stage), b_dst, ks * C::BLOCK_K,
+                                t.n_idx * BLOCK_N);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc =
+                        make_smem_desc(a_smem + stage * C::A_STAGE, 0, C::SBO, C::LAYOUT);
+                    const uint64_t bdesc =
+                        make_smem_desc(b_smem + stage * C::B_STAGE, 0, C::SBO, C::LAYOUT);
+#pragma unroll
+                    for (int k = 0; k < C::BLOCK_K / 16; ++k) {
+                        // +32 bytes (encoded >>4) per 16-element K slice inside the swizzle span
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                  (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (ks == num_k - 1) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;   // accumulator row == smem staging row
+        const int epi_tid = threadIdx.x - 64;  // 0..127
+        const int box_rows = p.tw * p.th * p.nb;
+        const int wi = row % p.tw;
+        const int hi = (row / p.tw) % p.th;
+        const int ni = row / (p.tw * p.th);
+        uint32_t sub_counter = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile(p, tile);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int col_base = t.n_idx * BLOCK_N;
+
+            for (int i = epi_tid; i < BLOCK_N; i += 128)
+                bias_s[i] = p.bias ? __ldg(p.bias + col_base + i) : 0.0f;
+
+            const bool row_ok = (row < box_rows) && (t.n0 + ni < p.Nimg) && (t.h0 + hi < p.Ho) &&
+                                (t.w0 + wi < p.Wo);
+            const long long pix =
+                (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
+            const __nv_bfloat16* res_row =
+                (p.residual && row_ok) ? p.residual + pix * p.ld_res + col_base : nullptr;
+            float* f32_row = (p.out_f32 && row_ok) ? p.out_f32 + pix * p.ld_f32 + col_base : nullptr;
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+
+#pragma unroll 1
+            for (int sub = 0; sub < BLOCK_N / 64; ++sub, ++sub_counter) {
+                const uint32_t buf = sub_counter & 1u;
+                if (epi_tid == 0) tma_store_wait_read<1>();  // buffer `buf` (2 stores ago) drained
+                named_bar_sync(1, 128);
+                uint8_t* st_row = st_gen + buf * kStageBufBytes + row * 128;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c0 = sub * 64 + half * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                  acc * BLOCK_N + c0,
+                              v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                        f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                        f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                        f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    }
+                    if (res_row) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 r4 =
+                                __ldg(reinterpret_cast<const uint4*>(res_row + c0) + q);
+                            const float2 r0 = unpack_bf16(r4.x), r1 = unpack_bf16(r4.y),
+                                         r2 = unpack_bf16(r4.z), r3 = unpack_bf16(r4.w);
+                            f[q * 8 + 0] += r0.x; f[q * 8 + 1] += r0.y;
+                            f[q * 8 + 2] += r1.x; f[q * 8 + 3] += r1.y;
+                            f[q * 8 + 4] += r2.x; f[q * 8 + 5] += r2.y;
+                            f[q * 8 + 6] += r3.x; f[q * 8 + 7] += r3.y;
+                        }
+                    }
+                    if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                    } else if (p.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    }
+                    if (f32_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(f32_row + c0 + j) =
+                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                    // bf16 pack into the 128B-swizzled staging tile (matches the C tensor map)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 o;
+                        o.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
+                        o.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+                        o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
+                        o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+                        const int chunk = (half * 4 + q) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(st_row + chunk * 16) = o;
+                    }
+                }
+                if (sub == BLOCK_N / 64 - 1) {
+                    // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (epi_tid == 0 && p.store_bf16) {
+                    tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, col_base + sub * 64,
+                                 t.w0, t.h0, t.n0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BLOCK_N, bool STEM>
+int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
+    using C = Cfg<BLOCK_N, STEM>;
+    static bool attr_set = false;
+    auto kfn = conv_gemm_kernel<BLOCK_N, STEM>;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_last_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
+                           cudaGetErrorString(e));
+            return -static_cast<int>(e);
+        }
+        attr_set = true;
+    }
+    kfn<<<g->grid, kNumThreads, C::SMEM_BYTES, stream>>>(g->p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("conv_gemm_kernel<%d,%d> launch: %s", BLOCK_N, (int)STEM,
+                       cudaGetErrorString(e));
+        return -static_cast<int>(e);
+    }
+    return 0;
+}
+
+int pick_block_n(int n, long long m_tiles, int sms) {
+    // widest N tile that divides N and still gives every SM at least one tile
+    if (n % 256 == 0 && m_tiles * (n / 256) >= sms) return 256;
+    if (n % 128 == 0 && m_tiles * (n / 128) >= sms) return 128;
+    if (n % 64 == 0 && (n % 128 != 0 || m_tiles * (n / 128) < sms)) return 64;
+    if (n % 128 == 0) return 128;
+    return 64;
+}
+
+int finish_plan(GemmLaunch* g, int block_n) {
+    ConvGemmParams& p = g->p;
+    g->block_n = block_n;
+    p.n_tiles_n = p.Cout / block_n;
+    const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_img;
+    const long long total = m_tiles * p.n_tiles_n;
+    if (total <= 0 || total > 0x7fffffffLL) {
+        set_last_error("gemm plan: bad tile count %lld", total);
+        return -1;
+    }
+    p.total_tiles = static_cast<int>(total);
+    const int sms = gemm_num_sms();
+    g->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    return 0;
+}
+
+}  // namespace
+
+int gemm_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
+              const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* Cout, long long ldc,
+              const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
+              int act) {
+    memset(g, 0, sizeof(*g));
+    if (M <= 0 || K <= 0 || N <= 0 || K % 64 != 0 || N % 64 != 0 || lda % 8 != 0 ||
+        (Cout && ldc % 8 != 0)) {
+        set_last_error("plan_gemm: unsupported shape M=%d N=%d K=%d lda=%lld ldc=%lld", M, N, K,
+                       lda, ldc);
+        return -1;
+    }
+    ConvGemmParams& p = g->p;
+    g->stem = 0;
+    p.bias = bias;
+    p.residual = residual;
+    p.ld_res = ld_res;
+    p.out_f32 = out_f32;
+    p.ld_f32 = ld_f32;
+    p.num_taps = 1;
+    p.kc_per_tap = K / 64;
+    p.taps[0] = TapDesc{0, 0, 0, 0};
+    p.tw = 128; p.th = 1; p.nb = 1;
+    p.tiles_w = (M + 127) / 128; p.tiles_h = 1; p.tiles_img = 1;
+    p.Wo = M; p.Ho = 1; p.Nimg = 1; p.Cout = N;
+    p.act = act;
+    p.store_bf16 = Cout != nullptr;
+    g->flops = 2.0 * M * static_cast<double>(N) * K;
+
+    const int bn = pick_block_n(N, p.tiles_w, gemm_num_sms());
+    {
+        uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+        uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * M, (uint64_t)lda * 2 * M};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_tensor_map(&p.a_map[0], A, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = encode_tensor_map(&p.b_map, W, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    if (Cout) {
+        uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
+        uint64_t str[3] = {(uint64_t)ldc * 2, (uint64_t)ldc * 2 * M, (uint64_t)ldc * 2 * M};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_tensor_map(&p.c_map, Cout, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    } else {
+        p.c_map = p.a_map[0];  // never dereferenced (store_bf16 == 0)
+    }
+    return finish_plan(g, bn);
+}
+
+int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Cin,
+              const __nv_bfloat16* Wt, int Cout, int ksize, int stride, const float* bias,
+              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act) {
+    if (ksize == 1 && stride == 1) {
+        const long long M = static_cast<long long>(N) * H * W;
+        if (M > 0x7fffffffLL) {
+            set_last_error("plan_conv: M too large");
+            return -1;
+        }
+        return plan_gemm(g, X, Cin, static_cast<int>(M), Cin, Wt, Cout, bias, Y, Cout, residual,
+                         Cout, nullptr, 0, act);
+    }
+    memset(g, 0, sizeof(*g));
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || Cin % 64 != 0 ||
+        Cout % 64 != 0 || H % stride != 0 || W % stride != 0 || N <= 0) {
+        set_last_error("plan_conv: unsupported conv k=%d s=%d Cin=%d Cout=%d H=%d W=%d", ksize,
+                       stride, Cin, Cout, H, W);
+        return -1;
+    }
+    ConvGemmParams& p = g->p;
+    g->stem = 0;
+    const int Ho = H / stride, Wo = W / stride;
+    p.bias = bias;
+    p.residual = residual;
+    p.ld_res = Cout;
+    p.out_f32 = nullptr;
+    p.ld_f32 = 0;
+    p.num_taps = ksize * ksize;
+    p.kc_per_tap = Cin / 64;
+    p.Wo = Wo; p.Ho = Ho; p.Nimg = N; p.Cout = Cout;
+    p.act = act;
+    p.store_bf16 = 1;
+    g->flops = 2.0 * N * Ho * Wo * static_cast<double>(Cout) * Cin * ksize * ksize;
+
+    // tile box: as many whole output rows (then whole images) as fit in 128 GEMM rows
+    p.tw = Wo < 128 ? Wo : 128;
+    p.th = 128 / p.tw;
+    if (p.th > Ho) p.th = Ho;
+    if (p.th < 1) p.th = 1;
+    p.nb = 1;
+    if (p.th == Ho && p.tw == Wo) {
+        p.nb = 128 / (p.tw * p.th);
+        if (p.nb < 1) p.nb = 1;
+        if (p.nb > N) p.nb = N;
+    }
+    p.tiles_w = (Wo + p.tw - 1) / p.tw;
+    p.tiles_h = (Ho + p.th - 1) / p.th;
+    p.tiles_img = (N + p.nb - 1) / p.nb;
+
+    // taps and A maps
+    if (stride == 1) {
+        int t = 0;
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s)
+                p.taps[t++] = TapDesc{0, (int8_t)(r - ksize / 2), (int8_t)(s - ksize / 2), 0};
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+        int rc = encode_tensor_map(&p.a_map[0], X, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    } else {
+        // stride 2: input row 2*ho + r - pad lives in parity phase a = (r - pad) & 1 at phase-row
+        // ho + floor((r - pad) / 2); same for columns.  Four phase views of the same tensor.
+        const int pad = ksize / 2;
+        int t = 0;
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s) {
+                const int dr = r - pad, ds = s - pad;
+                const int a = dr & 1, b = ds & 1;
+                const int qh = (dr - a) / 2, qw = (ds - b) / 2;  // floor division
+                p.taps[t++] = TapDesc{(int8_t)(a * 2 + b), (int8_t)qh, (int8_t)qw, 0};
+            }
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const __nv_bfloat16* base = X + (static_cast<long long>(a) * W + b) * Cin;
+                uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)N};
+                uint64_t str[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2,
+                                   (uint64_t)H * W * Cin * 2};
+                uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+                int rc = encode_tensor_map(&p.a_map[a * 2 + b], base, 2, 4, dims, str, box, 128);
+                if (rc) return rc;
+            }
+    }
+    const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_img;
+    const int bn = pick_block_n(Cout, m_tiles, gemm_num_sms());
+    {
+        const uint64_t Kt = static_cast<uint64_t>(Cin) * ksize * ksize;
+        uint64_t dims[2] = {Kt, (uint64_t)Cout};
+        uint64_t str[1] = {Kt * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = encode_tensor_map(&p.b_map, Wt, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2,
+                           (uint64_t)Ho * Wo * Cout * 2};
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    return finish_plan(g, bn);
+}
+
+int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
+              const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* Y, int act) {
+    memset(g, 0, sizeof(*g));
+    if (H % 2 != 0 || W % 2 != 0 || N <= 0) {
+        set_last_error("plan_stem: H, W must be even (got %d x %d)", H, W);
+        return -1;
+    }
+    ConvGemmParams& p = g->p;
+    g->stem = 1;
+    const int Ho = H / 2, Wo = W / 2;
+    const int Hp = H + 6, Wp = W + 8;  // 3 rows/cols of zero padding before, 3/5 after
+    p.bias = bias;
+    p.residual = nullptr;
+    p.out_f32 = nullptr;
+    p.num_taps = 7;
+    p.kc_per_tap = 1;
+    p.Wo = Wo; p.Ho = Ho; p.Nimg = N; p.Cout = 64;
+    p.act = act;
+    p.store_bf16 = 1;
+    g->flops = 2.0 * N * Ho * Wo * 64.0 * 147.0;
+    p.tw = Wo >= 16 ? 16 : Wo;
+    p.th = 128 / p.tw;
+    if (p.th > Ho) p.th = Ho;
+    p.nb = 1;
+    p.tiles_w = (Wo + p.tw - 1) / p.tw;
+    p.tiles_h = (Ho + p.th - 1) / p.th;
+    p.tiles_img = N;
+    {
+        // (k: 8 pixels x 4 channels = 32 contiguous bf16 starting at padded column 2*wo,
+        //  wo: stride 2 pixels = 16 B (windows overlap), ho: stride 2 padded rows, r: 1 padded row, n)
+        uint64_t dims[5] = {32, (uint64_t)Wo, (uint64_t)Ho, 7, (uint64_t)N};
+        uint64_t str[4] = {16, (uint64_t)2 * Wp * 8, (uint64_t)Wp * 8, (uint64_t)Hp * Wp * 8};
+        uint32_t box[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, 1, 1};
+        int rc = encode_tensor_map(&p.a_map[0], Xpad, 2, 5, dims, str, box, 64);
+        if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    }
+    {
+        uint64_t dims[2] = {7 * 32, 64};
+        uint64_t str[1] = {7 * 32 * 2};
+        uint32_t box[2] = {32, 64};
+        int rc = encode_tensor_map(&p.b_map, Wst, 2, 2, dims, str, box, 64);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t str[3] = {64 * 2, (uint64_t)Wo * 64 * 2, (uint64_t)Ho * Wo * 64 * 2};
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    return finish_plan(g, 64);
+}
+
+int launch_gemm(const GemmLaunch* g, cudaStream_t stream) {
+    if (g->stem) return launch_variant<64, true>(g, stream);
+    switch (g->block_n) {
+        case 64: return launch_variant<64, false>(g, stream);
+        case 128: return launch_variant<128, false>(g, stream);
+        case 256: return launch_variant<256, false>(g, stream);
+    }
+    set_last_error("launch_gemm: bad block_n %d", g->block_n);
+    return -1;
+}
+
+}  // namespace mrd

@@ -1,0 +1,76 @@
+// Implicit-GEMM launch plans.  One kernel family (conv_gemm_kernel) serves
+//   * plain GEMMs              C[M,N] = act(A[M,K] * W[N,K]^T + bias (+ residual))      (BERT, heads)
+//   * 1x1 / 3x3 convolutions   on NHWC bf16 activations, stride 1 or 2, BN folded       (ResNet50)
+//   * the 7x7/2 stem           through an overlapping-window 5-D tensor map             (ResNet50)
+// The A operand is always fetched by TMA from a (<=5)-D view of the activation tensor; im2col is
+// never materialised.  See DESIGN.md "K1/K2".
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mrd {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct TapDesc {
+    int8_t map;  // which A tensor map (stride-2 convs read one of 4 parity phases)
+    int8_t dh;   // row shift of the box, in (phase-)rows
+    int8_t dw;   // column shift of the box
+    int8_t pad_;
+};
+
+struct alignas(64) ConvGemmParams {
+    CUtensorMap a_map[4];
+    CUtensorMap b_map;
+    CUtensorMap c_map;
+    const float* bias;              // [Cout] fp32
+    const __nv_bfloat16* residual;  // NHWC / row-major, same logical shape as the output, or null
+    float* out_f32;                 // optional fp32 copy of the output, or null
+    long long ld_res;               // residual row (pixel) stride in elements
+    long long ld_f32;               // out_f32 row stride in elements
+    int num_taps;                   // 1, 7 (stem) or 9
+    int kc_per_tap;                 // K chunks (of BLOCK_K) per tap
+    TapDesc taps[9];
+    int tw, th, nb;                      // tile box: columns, rows, images  (tw*th*nb <= 128)
+    int tiles_w, tiles_h, tiles_img;     // tiles per output row / column / batch
+    int Wo, Ho, Nimg, Cout;              // logical output extent
+    int n_tiles_n;                       // Cout / BLOCK_N
+    int total_tiles;
+    int act;
+    int store_bf16;                      // 1: write bf16 output through c_map
+};
+
+struct GemmLaunch {
+    ConvGemmParams p;
+    int block_n;  // 64, 128 or 256
+    int stem;     // 1: 5-D overlapping-window A map, BLOCK_K = 32
+    int grid;
+    double flops;  // algorithmic FLOPs (2*M*N*K, un-padded), for reporting
+};
+
+// Plain GEMM.  A: [M,K] bf16 with row stride lda; W: [N,K] bf16 (nn.Linear layout); C: [M,N] bf16
+// with row stride ldc (may be null when only out_f32 is wanted).  K % 64 == 0, N % 64 == 0.
+int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K,
+              const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* C, long long ldc,
+              const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
+              int act);
+
+// ksize in {1,3}, stride in {1,2}, padding = ksize/2.  X: [N,H,W,Cin] bf16, Wt: [Cout][k][k][Cin]
+// bf16 (BN already folded), Y: [N,H/stride,W/stride,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0.
+int plan_conv(GemmLaunch* out, const __nv_bfloat16* X, int N, int H, int W, int Cin,
+              const __nv_bfloat16* Wt, int Cout, int ksize, int stride, const float* bias,
+              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act);
+
+// 7x7 stride-2 pad-3 stem.  Xpad: [N][H+6][W+8][4] bf16 (zero border, channel 3 zero),
+// Wst: [64][7][32] bf16 (tap row r, then 8 pixels x 4 channels; BN folded), Y: [N,H/2,W/2,64].
+int plan_stem(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W,
+              const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* Y, int act);
+
+int launch_gemm(const GemmLaunch* g, cudaStream_t stream);
+
+int gemm_num_sms();
+
+}  // namespace mrd

@@ -1,0 +1,230 @@
+"""Host-side wrapper of one mrd_ctx (C ABI, include/mrd_b200.h): weight hand-off and forwards.
+
+PyTorch is plumbing here: it owns the nn.Parameters (so state_dicts/checkpoints of the reference
+load unchanged), allocates the output tensors and supplies the CUDA stream.  All arithmetic runs in
+libmrd_b200.so.  An Engine refuses to run anywhere but on an sm_100 CUDA device.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_MASK_CODES = {
+    torch.int64: _lib.DT_I64,
+    torch.int32: _lib.DT_I32,
+    torch.float32: _lib.DT_F32,
+    torch.uint8: _lib.DT_U8,
+    torch.bool: _lib.DT_U8,
+    torch.bfloat16: _lib.DT_BF16,
+}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Engine:
+    """One mrd_ctx bound to one CUDA device, fed from an nn.Module's parameters.
+
+    `groups` maps the module-tree prefixes of the owning module onto the canonical state_dict
+    prefixes the library expects ("cnn_encoder.", "text_encoder.", "fusion.", "classifier."), e.g. a
+    standalone CNNEncoder passes {"": "cnn_encoder."}.
+    """
+
+    def __init__(self, device: torch.device, options: Optional[Dict[str, float]] = None):
+        if device.type != "cuda":
+            raise _lib.MrdError(
+                f"the B200 path runs on CUDA devices only (module is on '{device}'); "
+                "there is no CPU fallback - use the reference implementation on CPU")
+        self.lib = _lib.load()
+        self.device = device
+        self._sig = None
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.mrd_ctx_create(C.byref(self._ctx)), "mrd_ctx_create")
+            for k, v in (options or {}).items():
+                _lib.check(self.lib.mrd_ctx_set_option(self._ctx, k.encode(), float(v)),
+                           f"mrd_ctx_set_option({k})")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None) is not None and self._ctx.value:
+                self.lib.mrd_ctx_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration / stats
+    def configure(self, img_chunk: int = 0, seq_chunk_tokens: int = 0) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrd_ctx_configure(self._ctx, int(img_chunk), int(seq_chunk_tokens)),
+                       "mrd_ctx_configure")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mrd_ctx_launch_count(self._ctx))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.mrd_ctx_device_bytes(self._ctx))
+
+    # ------------------------------------------------------------------ weights
+    def sync_weights(self, named: Iterable[Tuple[str, torch.Tensor]]) -> bool:
+        """Re-pack the library's weights iff a tensor was replaced or written since the last call.
+
+        named: (canonical state_dict name, tensor) pairs.  Returns True when a re-pack happened.
+        """
+        named = [(n, t) for n, t in named if t.is_floating_point()]
+        sig = tuple((n, t.data_ptr(), t._version, t.dtype) for n, t in named)
+        if sig == self._sig:
+            return False
+        keep = []  # fp32 contiguous views / temporaries alive until the packing kernels finished
+        n = len(named)
+        names = (C.c_char_p * n)()
+        ptrs = (C.c_void_p * n)()
+        shapes = (C.c_longlong * (4 * n))()
+        for i, (name, t) in enumerate(named):
+            if t.device != self.device:
+                raise _lib.MrdError(f"parameter {name} is on {t.device}, engine is on {self.device}")
+            if t.dim() > 4:
+                raise _lib.MrdError(f"parameter {name} has {t.dim()} dims")
+            x = t.detach()
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            keep.append(x)
+            names[i] = name.encode()
+            ptrs[i] = x.data_ptr()
+            for j, d in enumerate(x.shape):
+                shapes[4 * i + j] = d
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrd_ctx_load_weights(self._ctx, n, names, ptrs, shapes,
+                                                     _stream(self.device)), "mrd_ctx_load_weights")
+        self._sig = sig
+        return True
+
+    # ------------------------------------------------------------------ input normalisation
+    def _images(self, images: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        if images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError(f"images must be [B,3,H,W], got {tuple(images.shape)}")
+        if images.device != self.device:
+            raise _lib.MrdError(f"images are on {images.device}, model is on {self.device}")
+        if images.dtype not in (torch.float32, torch.bfloat16):
+            images = images.float()
+        images = images.contiguous()
+        return images, (_lib.DT_BF16 if images.dtype == torch.bfloat16 else _lib.DT_F32)
+
+    def _text(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]):
+        if input_ids.dim() != 2:
+            raise ValueError(f"input_ids must be [B,S], got {tuple(input_ids.shape)}")
+        if input_ids.device != self.device:
+            raise _lib.MrdError(f"input_ids are on {input_ids.device}, model is on {self.device}")
+        ids = input_ids if input_ids.dtype == torch.int64 else input_ids.long()
+        ids = ids.contiguous()
+        mask, code = None, _lib.DT_I64
+        if attention_mask is not None:
+            if attention_mask.shape != input_ids.shape:
+                raise ValueError("attention_mask must have the shape of input_ids")
+            mask = attention_mask.to(self.device)
+            if mask.dtype not in _MASK_CODES:
+                mask = mask.float() if mask.is_floating_point() else mask.long()
+            mask = mask.contiguous()
+            code = _MASK_CODES[mask.dtype]
+        return ids, mask, code
+
+    def _f32(self, *shape) -> torch.Tensor:
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ forwards
+    def cnn_encoder(self, images, emb_dim: int, want_pooled=False, want_map=False):
+        images, code = self._images(images)
+        B, _, H, W = images.shape
+        emb = self._f32(B, emb_dim)
+        pooled = self._f32(B, 2048) if want_pooled else None
+        fmap = self._f32(B, 2048, H // 32, W // 32) if want_map else None
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_cnn_encoder_fwd(self._ctx, images.data_ptr(), code, B, H, W,
+                                                        emb.data_ptr(), _ptr(pooled), _ptr(fmap),
+                                                        _stream(self.device)), "mrd_cnn_encoder_fwd")
+        return emb, pooled, fmap
+
+    def text_encoder(self, input_ids, attention_mask, hidden: int = 768, want_hidden=False):
+        ids, mask, code = self._text(input_ids, attention_mask)
+        B, S = ids.shape
+        cls = self._f32(B, hidden)
+        last = self._f32(B, S, hidden) if want_hidden else None
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_text_encoder_fwd(self._ctx, ids.data_ptr(), _ptr(mask), code,
+                                                         B, S, cls.data_ptr(), _ptr(last),
+                                                         _stream(self.device)), "mrd_text_encoder_fwd")
+        return cls, last
+
+    def fusion(self, img_emb, txt_emb, hidden_dim: int, heads: int):
+        if img_emb.dim() != 2 or txt_emb.dim() != 2 or img_emb.shape[0] != txt_emb.shape[0]:
+            raise ValueError("fusion expects [B,Di] and [B,Dt] embeddings")
+        img = img_emb.to(self.device, torch.float32).contiguous()
+        txt = txt_emb.to(self.device, torch.float32).contiguous()
+        B = img.shape[0]
+        fused = self._f32(B, hidden_dim)
+        a1 = self._f32(B, heads, 1, 1)
+        a2 = self._f32(B, heads, 1, 1)
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_fusion_fwd(self._ctx, img.data_ptr(), txt.data_ptr(), B,
+                                                   fused.data_ptr(), a1.data_ptr(), a2.data_ptr(),
+                                                   _stream(self.device)), "mrd_fusion_fwd")
+        return fused, a1, a2
+
+    def head(self, x, num_classes: int, want_probs=True):
+        if x.dim() != 2:
+            raise ValueError("classification head expects [B,D] features")
+        x = x.to(self.device, torch.float32).contiguous()
+        B = x.shape[0]
+        logits = self._f32(B, num_classes)
+        probs = self._f32(B, num_classes) if want_probs else None
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_head_fwd(self._ctx, x.data_ptr(), B, logits.data_ptr(),
+                                                 _ptr(probs), _stream(self.device)), "mrd_head_fwd")
+        return logits, probs
+
+    def multimodal(self, images, input_ids, attention_mask, dims, want_embeddings=False,
+                   logits_out: Optional[torch.Tensor] = None):
+        """dims = (num_classes, img_emb, txt_emb, fused, heads).  logits_out: optional preallocated
+        f32 [B,num_classes] slice (e.g. this rank's slot of an all-gather buffer)."""
+        images, icode = self._images(images)
+        ids, mask, mcode = self._text(input_ids, attention_mask)
+        B, _, H, W = images.shape
+        if ids.shape[0] != B:
+            raise ValueError(f"batch mismatch: {B} images vs {ids.shape[0]} token rows")
+        S = ids.shape[1]
+        nc, di, dt, df, heads = dims
+        if logits_out is not None:
+            if (logits_out.shape != (B, nc) or logits_out.dtype != torch.float32
+                    or not logits_out.is_contiguous() or logits_out.device != self.device):
+                raise ValueError("logits_out must be a contiguous f32 [B,num_classes] tensor on the model device")
+            logits = logits_out
+        else:
+            logits = self._f32(B, nc)
+        probs = self._f32(B, nc)
+        img_e = txt_e = fused = a1 = a2 = None
+        if want_embeddings:
+            img_e, txt_e, fused = self._f32(B, di), self._f32(B, dt), self._f32(B, df)
+            a1, a2 = self._f32(B, heads, 1, 1), self._f32(B, heads, 1, 1)
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_multimodal_fwd(
+                    self._ctx, images.data_ptr(), icode, ids.data_ptr(), _ptr(mask), mcode, B, H, W, S,
+                    logits.data_ptr(), probs.data_ptr(), _ptr(img_e), _ptr(txt_e), _ptr(fused),
+                    _ptr(a1), _ptr(a2), _stream(self.device)), "mrd_multimodal_fwd")
+        return logits, probs, img_e, txt_e, fused, a1, a2

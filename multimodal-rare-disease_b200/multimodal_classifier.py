@@ -1,0 +1,193 @@
+"""MultimodalClassifier - drop-in for the reference's src/multimodal_classifier.py.
+
+Same classes, constructor arguments, attributes, state_dict keys (`cnn_encoder.*`, `text_encoder.*`,
+`fusion.*`, `classifier.classifier.{0,3,6}.*`) and the same forward/predict contracts
+(src/multimodal_classifier.py:131-202).  One forward = one call into libmrd_b200.so
+(mrd_multimodal_fwd): ResNet50 + BERT-base + attention fusion + head + softmax on the caller's CUDA
+stream, tiled into L2-sized micro-batches inside the library.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._module import B200Module
+from .cnn_encoder import CNNEncoder
+from .config import Config, get_config
+from .fusion_model import MultimodalFusion
+from .text_encoder import TextEncoder
+
+_ACT = {"relu": _lib.ACT_RELU, "gelu": _lib.ACT_GELU}
+
+
+class ClassificationHead(B200Module):
+    """Linear/activation/dropout stack (src/multimodal_classifier.py:16-83)."""
+
+    _mrd_groups = {"": "classifier."}
+
+    def __init__(self, input_dim: int, hidden_dims: List[int] = (512, 256), num_classes: int = 10,
+                 dropout: float = 0.4, activation: str = "relu"):
+        super().__init__()
+        self.num_classes = num_classes
+        self.activation = activation if activation in ("relu", "gelu", "leaky_relu") else "relu"
+        layers: List[nn.Module] = []
+        prev = input_dim
+        for h in hidden_dims:
+            layers += [nn.Linear(prev, h), self._get_activation(activation), nn.Dropout(dropout)]
+            prev = h
+        layers.append(nn.Linear(prev, num_classes))
+        self.classifier = nn.Sequential(*layers)
+
+    @staticmethod
+    def _get_activation(name: str) -> nn.Module:
+        if name == "gelu":
+            return nn.GELU()
+        if name == "leaky_relu":
+            return nn.LeakyReLU(0.1, inplace=True)
+        return nn.ReLU(inplace=True)
+
+    def _mrd_options(self):
+        if self.activation not in _ACT:
+            raise NotImplementedError(f"activation {self.activation!r} is outside the B200 hot path")
+        return {"head_act": _ACT[self.activation]}
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        logits, _ = self._engine().head(x, self.num_classes, want_probs=False)
+        return logits
+
+
+class MultimodalClassifier(B200Module):
+    _mrd_groups = {"cnn_encoder.": "cnn_encoder.", "text_encoder.": "text_encoder.",
+                   "fusion.": "fusion.", "classifier.": "classifier."}
+
+    def __init__(self, config: Optional[Config] = None, *, random_init: bool = False):
+        """random_init=True: BioBERT-base shaped text encoder without the hub download and no
+        ImageNet download (benchmarks / tests on air-gapped machines).  Default = reference."""
+        super().__init__()
+        config = get_config() if config is None else config
+        self.config = config
+        cnn_cfg = config.cnn_encoder
+        if random_init and getattr(cnn_cfg, "pretrained", False):
+            import copy
+
+            cnn_cfg = copy.copy(cnn_cfg)
+            cnn_cfg.pretrained = False
+        self.cnn_encoder = CNNEncoder(cnn_cfg)
+        self.text_encoder = TextEncoder(config.text_encoder, random_init=random_init)
+        self.fusion = MultimodalFusion(config.fusion)
+        self.classifier = ClassificationHead(
+            input_dim=config.fusion.hidden_dim,
+            hidden_dims=config.classifier.hidden_dims,
+            num_classes=config.classifier.num_classes,
+            dropout=config.classifier.dropout,
+            activation=config.classifier.activation,
+        )
+        self.image_embedding_dim = config.cnn_encoder.embedding_dim
+        self.text_embedding_dim = config.text_encoder.embedding_dim
+        self.fusion_dim = config.fusion.hidden_dim
+        self.num_classes = config.classifier.num_classes
+
+    def _mrd_options(self):
+        opts = {}
+        for m in (self.text_encoder, self.fusion, self.classifier):
+            opts.update(m._mrd_options())
+        return opts
+
+    def _dims(self):
+        return (self.num_classes, self.cnn_encoder.embedding_dim, self.text_encoder.embedding_dim,
+                self.fusion_dim, self.config.fusion.num_attention_heads)
+
+    def forward(self, images: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                return_embeddings: bool = False, *, logits_out: Optional[torch.Tensor] = None
+                ) -> Dict[str, torch.Tensor]:
+        """images [B,3,224,224], input_ids/attention_mask [B,S] -> {"logits","probs"} (+ embeddings
+        and the fusion attention weights when return_embeddings=True), all fp32 on the model device."""
+        self.text_encoder._check()
+        logits, probs, img_e, txt_e, fused, a1, a2 = self._engine().multimodal(
+            images, input_ids, attention_mask, self._dims(), want_embeddings=return_embeddings,
+            logits_out=logits_out)
+        out = {"logits": logits, "probs": probs}
+        if return_embeddings:
+            out["image_embedding"] = img_e
+            out["text_embedding"] = txt_e
+            out["fused_embedding"] = fused
+            out["attention_info"] = {"image_to_text_attention": a1, "text_to_image_attention": a2}
+        return out
+
+    def predict(self, images, input_ids, attention_mask) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.eval()
+        with torch.no_grad():
+            probs = self.forward(images, input_ids, attention_mask)["probs"]
+            confidence, predicted = torch.max(probs, dim=-1)
+        return predicted, confidence
+
+
+class ImageOnlyClassifier(B200Module):
+    """src/multimodal_classifier.py:205-246."""
+
+    _mrd_groups = {"cnn_encoder.": "cnn_encoder.", "classifier.": "classifier."}
+
+    def __init__(self, config: Optional[Config] = None):
+        super().__init__()
+        config = get_config() if config is None else config
+        self.cnn_encoder = CNNEncoder(config.cnn_encoder)
+        self.classifier = ClassificationHead(config.cnn_encoder.embedding_dim,
+                                             config.classifier.hidden_dims,
+                                             config.classifier.num_classes,
+                                             config.classifier.dropout, config.classifier.activation)
+
+    def _mrd_options(self):
+        return self.classifier._mrd_options()
+
+    def forward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        eng = self._engine()
+        emb, _, _ = eng.cnn_encoder(images, self.cnn_encoder.embedding_dim)
+        logits, probs = eng.head(emb, self.classifier.num_classes)
+        return {"logits": logits, "probs": probs}
+
+
+class TextOnlyClassifier(B200Module):
+    """src/multimodal_classifier.py:249-293."""
+
+    _mrd_groups = {"text_encoder.": "text_encoder.", "classifier.": "classifier."}
+
+    def __init__(self, config: Optional[Config] = None, *, random_init: bool = False):
+        super().__init__()
+        config = get_config() if config is None else config
+        self.text_encoder = TextEncoder(config.text_encoder, random_init=random_init)
+        self.classifier = ClassificationHead(config.text_encoder.embedding_dim,
+                                             config.classifier.hidden_dims,
+                                             config.classifier.num_classes,
+                                             config.classifier.dropout, config.classifier.activation)
+
+    def _mrd_options(self):
+        opts = self.text_encoder._mrd_options()
+        opts.update(self.classifier._mrd_options())
+        return opts
+
+    def forward(self, input_ids, attention_mask) -> Dict[str, torch.Tensor]:
+        self.text_encoder._check()
+        eng = self._engine()
+        cls, _ = eng.text_encoder(input_ids, attention_mask, self.text_encoder.embedding_dim)
+        logits, probs = eng.head(cls, self.classifier.num_classes)
+        return {"logits": logits, "probs": probs}
+
+
+def create_multimodal_classifier(num_classes: int = 10, cnn_backbone: str = "resnet50",
+                                 text_model: str = "dmis-lab/biobert-base-cased-v1.2",
+                                 fusion_type: str = "attention", **kwargs) -> MultimodalClassifier:
+    cfg = get_config()
+    cfg.classifier.num_classes = num_classes
+    cfg.cnn_encoder.backbone = cnn_backbone
+    cfg.text_encoder.model_name = text_model
+    cfg.fusion.fusion_type = fusion_type
+    return MultimodalClassifier(cfg, **kwargs)
+
+
+def create_baseline_classifiers(config: Optional[Config] = None
+                                ) -> Tuple[ImageOnlyClassifier, TextOnlyClassifier]:
+    return ImageOnlyClassifier(config), TextOnlyClassifier(config)

@@ -1,0 +1,261 @@
+"""Per-kernel parity through the C ABI (include/mrd_b200.h) against the same op in plain PyTorch
+fp32 on the same bf16-rounded operands.  Tolerances: outputs are bf16 (8 mantissa bits), so the bar
+is |err| <= 2^-7 * |ref| + a small absolute term that covers fp32 accumulation-order differences."""
+
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(lib, rc):
+    assert rc == 0, (rc, lib.mrd_last_error())
+
+
+def _close(out, ref, rel=2 ** -7, abs_=1e-2, what=""):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs()
+    bound = rel * ref.abs() + abs_
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance; max err "
+                           f"{err.max().item():.4g} at ref {ref.flatten()[err.argmax()].item():.4g}")
+
+
+# ------------------------------------------------------------------ GEMM (K2)
+@pytest.mark.parametrize("M,N,K,act,res,f32", [
+    (128, 64, 64, 0, False, False),
+    (256, 128, 128, 1, False, True),
+    (300, 768, 768, 0, True, False),        # ragged M, BERT out-proj + residual
+    (1024, 2304, 768, 0, False, False),     # fused QKV
+    (777, 3072, 768, 2, False, False),      # FFN1 + exact GELU
+    (512, 768, 3072, 0, True, True),        # FFN2 + residual, long K
+    (5, 512, 2048, 1, False, True),         # tiny batch (projection)
+    (20000, 256, 64, 1, False, False),      # ResNet layer1-like 1x1 conv, many tiles (persistence)
+    (4096, 64, 256, 1, False, False),       # narrow N
+])
+def test_gemm(lib, cuda, M, N, K, act, res, f32):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device=cuda, generator=g).to(BF)
+    W = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(BF)
+    bias = torch.randn(N, device=cuda, generator=g)
+    R = torch.randn(M, N, device=cuda, generator=g).to(BF) if res else None
+    C = torch.full((M, N), float("nan"), device=cuda, dtype=BF)
+    C32 = torch.full((M, N), float("nan"), device=cuda) if f32 else None
+    _check(lib, lib.mrd_gemm_bf16(A.data_ptr(), K, M, K, W.data_ptr(), N, bias.data_ptr(), C.data_ptr(),
+                                  N, R.data_ptr() if res else None, N,
+                                  C32.data_ptr() if f32 else None, N, act, _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    if res:
+        ref = ref + R.float()
+    if act == 1:
+        ref = F.relu(ref)
+    elif act == 2:
+        ref = F.gelu(ref)
+    _close(C, ref, what="gemm bf16 out")
+    if f32:
+        _close(C32, ref, rel=1e-4, abs_=2e-3, what="gemm f32 out")
+
+
+def test_gemm_strided(lib, cuda):
+    """A rows taken with a stride (CLS rows of a [B,S,768] tensor), C written into a wider buffer."""
+    B, S, K, N = 37, 16, 768, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(B, S, K, device=cuda, generator=g).to(BF)
+    W = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(BF)
+    bias = torch.randn(N, device=cuda, generator=g)
+    C = torch.zeros(B, 2 * N, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_gemm_bf16(X.data_ptr(), S * K, B, K, W.data_ptr(), N, bias.data_ptr(),
+                                  C[:, N:].data_ptr(), 2 * N, None, 0, None, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = X[:, 0].float() @ W.float().t() + bias
+    _close(C[:, N:], ref, what="strided gemm")
+    assert (C[:, :N] == 0).all()
+
+
+def test_gemm_rejects_bad_shapes(lib, cuda):
+    A = torch.zeros(8, 100, device=cuda, dtype=BF)
+    rc = lib.mrd_gemm_bf16(A.data_ptr(), 100, 8, 100, A.data_ptr(), 64, None, A.data_ptr(), 64, None,
+                           0, None, 0, 0, _stream())
+    assert rc != 0 and b"unsupported" in lib.mrd_last_error()
+
+
+# ------------------------------------------------------------------ convolutions (K1)
+def _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, device=cuda, generator=g).to(BF)
+    w = (torch.randn(Cout, Cin, k, k, device=cuda, generator=g) / math.sqrt(Cin * k * k)).to(BF)
+    bias = torch.randn(Cout, device=cuda, generator=g)
+    Ho, Wo = H // stride, W // stride
+    r = torch.randn(N, Cout, Ho, Wo, device=cuda, generator=g).to(BF) if res else None
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_ohwi = w.permute(0, 2, 3, 1).contiguous()
+    r_nhwc = r.permute(0, 2, 3, 1).contiguous() if res else None
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_conv2d_nhwc_bf16(x_nhwc.data_ptr(), N, H, W, Cin, w_ohwi.data_ptr(), Cout, k,
+                                         stride, bias.data_ptr(), y.data_ptr(),
+                                         r_nhwc.data_ptr() if res else None, act, _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=k // 2)
+    if res:
+        ref = ref + r.float()
+    if act == 1:
+        ref = F.relu(ref)
+    _close(y.permute(0, 3, 1, 2), ref, what=f"conv k{k} s{stride} {Cin}->{Cout} {H}x{W}")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,act,res", [
+    (2, 56, 56, 64, 64, 1, 1, 1, False),      # layer1 conv1
+    (2, 56, 56, 64, 64, 3, 1, 1, False),      # layer1 conv2 (rows-of-56 tiles, zero halo)
+    (2, 56, 56, 64, 256, 1, 1, 1, True),      # layer1 conv3 + identity
+    (3, 56, 56, 128, 128, 3, 2, 1, False),    # layer2.0 conv2, stride 2 (parity-phase views)
+    (3, 56, 56, 256, 512, 1, 2, 0, False),    # layer2.0 downsample, 1x1 stride 2
+    (2, 28, 28, 128, 128, 3, 1, 1, False),    # layer2 conv2
+    (5, 14, 14, 256, 256, 3, 1, 1, False),    # layer3 conv2 (partial tile rows)
+    (5, 14, 14, 512, 512, 3, 2, 1, False),    # layer4.0 conv2
+    (7, 7, 7, 512, 512, 3, 1, 1, False),      # layer4 conv2 (several images per tile, odd count)
+    (3, 7, 7, 512, 2048, 1, 1, 1, True),      # layer4 conv3 + identity
+    (1, 32, 64, 64, 64, 3, 1, 0, False),      # non-square
+])
+def test_conv(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res):
+    _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 224, 224), (1, 64, 96), (3, 32, 32)])
+def test_stem(lib, cuda, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(H)
+    x = torch.randn(N, 3, H, W, device=cuda, generator=g)
+    w = torch.randn(64, 3, 7, 7, device=cuda, generator=g) / math.sqrt(147)
+    gamma = 0.5 + torch.rand(64, device=cuda, generator=g)
+    beta = torch.randn(64, device=cuda, generator=g) * 0.1
+    mean = torch.randn(64, device=cuda, generator=g) * 0.1
+    var = 0.5 + torch.rand(64, device=cuda, generator=g)
+    # host-side packing equivalent to pack_stem_bn (tested separately through the engine)
+    scale = gamma / torch.sqrt(var + 1e-5)
+    wf = (w * scale.view(-1, 1, 1, 1))
+    wst = torch.zeros(64, 7, 8, 4, device=cuda)
+    wst[:, :, :7, :3] = wf.permute(0, 2, 3, 1)  # [co][r][s][c]
+    wst = wst.view(64, 7, 32).to(BF).contiguous()
+    bias = (beta - mean * scale).contiguous()
+    xpad = torch.full((N, H + 6, W + 8, 4), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_repack_images(x.data_ptr(), 2, N, H, W, xpad.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(xpad[:, 3:3 + H, 3:3 + W, :3], x.permute(0, 2, 3, 1).to(BF))
+    assert (xpad[:, :3] == 0).all() and (xpad[:, :, :3] == 0).all() and (xpad[..., 3] == 0).all()
+    assert (xpad[:, 3 + H:] == 0).all() and (xpad[:, :, 3 + W:] == 0).all()
+    y = torch.full((N, H // 2, W // 2, 64), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_stem_conv_bf16(xpad.data_ptr(), N, H, W, wst.data_ptr(), bias.data_ptr(),
+                                       y.data_ptr(), 1, _stream()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.to(BF).float(), wst.view(64, 7, 8, 4)[:, :, :7, :3].permute(0, 3, 1, 2).float(),
+                          bias, stride=2, padding=3))
+    _close(y.permute(0, 3, 1, 2), ref, what="stem")
+
+
+# ------------------------------------------------------------------ pooling
+def test_maxpool(lib, cuda):
+    x = torch.randn(3, 64, 112, 112, device=cuda).to(BF)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    y = torch.empty(3, 56, 56, 64, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_maxpool3x3s2(xn.data_ptr(), 3, 112, 112, 64, y.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    ref = F.max_pool2d(x.float(), 3, 2, 1)
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), ref)  # max of bf16 values is exact
+
+
+def test_avgpool(lib, cuda):
+    x = torch.randn(5, 49, 2048, device=cuda).to(BF)
+    yb = torch.empty(5, 2048, device=cuda, dtype=BF)
+    yf = torch.empty(5, 2048, device=cuda)
+    _check(lib, lib.mrd_global_avgpool(x.data_ptr(), 5, 49, 2048, yb.data_ptr(), yf.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    ref = x.float().mean(1)
+    _close(yf, ref, rel=1e-5, abs_=1e-5, what="avgpool f32")
+    _close(yb, ref, what="avgpool bf16")
+
+
+# ------------------------------------------------------------------ LayerNorm / embeddings
+@pytest.mark.parametrize("rows,width,res,eps", [(1000, 768, True, 1e-12), (77, 512, False, 1e-5),
+                                                (9, 256, True, 1e-5), (33, 1024, False, 1e-5)])
+def test_layernorm(lib, cuda, rows, width, res, eps):
+    x = (torch.randn(rows, width, device=cuda) * 3 + 1).to(BF)
+    r = torch.randn(rows, width, device=cuda).to(BF) if res else None
+    gamma = torch.rand(width, device=cuda) + 0.5
+    beta = torch.randn(width, device=cuda)
+    yb = torch.empty(rows, width, device=cuda, dtype=BF)
+    yf = torch.empty(rows, width, device=cuda)
+    _check(lib, lib.mrd_layernorm_residual(x.data_ptr(), width, r.data_ptr() if res else None, width,
+                                           gamma.data_ptr(), beta.data_ptr(), eps, rows, width,
+                                           yb.data_ptr(), width, yf.data_ptr(), width, _stream()))
+    torch.cuda.synchronize()
+    s = x.float() + (r.float() if res else 0)
+    ref = F.layer_norm(s, (width,), gamma, beta, eps)
+    _close(yf, ref, rel=1e-4, abs_=1e-4, what="ln f32")
+    _close(yb, ref, what="ln bf16")
+
+
+def test_bert_embed(lib, cuda):
+    B, S, V = 4, 50, 1000
+    ids = torch.randint(0, V, (B, S), device=cuda)
+    word = torch.randn(V, 768, device=cuda).to(BF)
+    pos_type = torch.randn(512, 768, device=cuda)
+    gamma = torch.rand(768, device=cuda) + 0.5
+    beta = torch.randn(768, device=cuda)
+    y = torch.empty(B * S, 768, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_bert_embed_layernorm(ids.data_ptr(), B, S, word.data_ptr(), pos_type.data_ptr(),
+                                             gamma.data_ptr(), beta.data_ptr(), 1e-12, V, y.data_ptr(),
+                                             _stream()))
+    torch.cuda.synchronize()
+    e = word.float()[ids] + pos_type[:S].unsqueeze(0)
+    ref = F.layer_norm(e, (768,), gamma, beta, 1e-12).view(B * S, 768)
+    _close(y, ref, what="bert embed")
+
+
+# ------------------------------------------------------------------ attention (K3)
+@pytest.mark.parametrize("B,S,heads,lengths", [
+    (2, 128, 12, None),
+    (3, 128, 12, [128, 70, 1]),
+    (2, 512, 12, [512, 65]),       # whole key blocks skipped
+    (3, 48, 4, [48, 33, 5]),       # S < 64: BLOCK_M = 64 path, ragged
+    (2, 200, 12, [200, 129]),      # S not a multiple of 64
+])
+def test_attention(lib, cuda, B, S, heads, lengths):
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    D = heads * 64
+    qkv = torch.randn(B * S, 3 * D, device=cuda, generator=g).to(BF)
+    qkv[:, :D] *= 0.125  # the engine folds 1/sqrt(64) into Wq
+    mask = torch.ones(B, S, device=cuda, dtype=torch.long)
+    if lengths:
+        for b, L in enumerate(lengths):
+            mask[b, L:] = 0
+    bias = torch.empty(B, S, device=cuda)
+    _check(lib, lib.mrd_mask_to_bias(mask.data_ptr(), 0, B, S, bias.data_ptr(), _stream()))
+    out = torch.full((B * S, D), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_attention_bf16(qkv.data_ptr(), bias.data_ptr() if lengths else None, B, S, heads,
+                                       out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(bias == 0, mask != 0) and torch.isinf(bias[mask == 0]).all()
+    q, k, v = [t.view(B, S, heads, 64).transpose(1, 2).float() for t in qkv.view(B, S, 3 * D).split(D, -1)]
+    sc = q @ k.transpose(-1, -2) + bias.view(B, 1, 1, S)
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, D)
+    _close(out, ref, rel=2 ** -6, abs_=2e-2, what="attention")
+
+
+@pytest.mark.parametrize("dtype,code", [(torch.int64, 0), (torch.int32, 1), (torch.float32, 2),
+                                        (torch.bool, 3), (torch.bfloat16, 4)])
+def test_mask_dtypes(lib, cuda, dtype, code):
+    m = (torch.rand(3, 77, device=cuda) > 0.4)
+    bias = torch.empty(3, 77, device=cuda)
+    mm = m.to(dtype)
+    _check(lib, lib.mrd_mask_to_bias(mm.data_ptr(), code, 3, 77, bias.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(bias == 0, m)
