@@ -100,6 +100,13 @@ int mrd_multimodal_fwd(mrd_ctx* ctx, const void* images, int img_dtype, const lo
                        float* probs, float* img_emb, float* txt_emb, float* fused, float* attn_i2t,
                        float* attn_t2i, void* stream);
 
+/* Profile mode: while enabled every kernel launch of a forward is bracketed by CUDA events on the
+ * launching stream.  mrd_ctx_profile(ctx, 1) clears earlier records and starts; _report synchronises
+ * and writes one CSV line per kernel label into buf: label,category(0 tensor|1 attention|2 memory),
+ * launches,total_ms,algorithmic_flops,algorithmic_bytes.  Used by bench.py for the roofline object. */
+int mrd_ctx_profile(mrd_ctx* ctx, int enable);
+int mrd_ctx_profile_report(mrd_ctx* ctx, char* buf, int cap);
+
 /* Kernel launches issued by this context since creation (for the bench's gpu_launches claim). */
 long long mrd_ctx_launch_count(const mrd_ctx* ctx);
 /* Bytes of device memory the context currently owns (weights + workspace). */

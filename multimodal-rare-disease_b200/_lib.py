@@ -41,6 +41,8 @@ SIGNATURES = {
     "mrd_head_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "mrd_multimodal_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp]),
+    "mrd_ctx_profile": (_i, [_vp, _i]),
+    "mrd_ctx_profile_report": (_i, [_vp, C.c_char_p, _i]),
     "mrd_ctx_launch_count": (_ll, [_vp]),
     "mrd_ctx_device_bytes": (_ll, [_vp]),
     "mrd_gemm_bf16": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),

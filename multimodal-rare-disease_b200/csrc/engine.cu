@@ -96,9 +96,26 @@ struct BatchPlan {
 
 }  // namespace
 
+struct ProfRecord {
+    const char* label = "";
+    int cat = 0;
+    double flops = 0, bytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
 struct mrd_ctx {
     int device = 0;
     long long launches = 0;
+    bool profiling = false;
+    std::vector<ProfRecord> prof;
+    std::vector<int> block_stage;          // ResNet stage (1..4) of each bottleneck
+    std::map<std::string, std::string> label_pool;
+    const char* label(const char* a, const char* b) {  // interned "a" + "b"
+        std::string k = std::string(a) + b;
+        auto it = label_pool.find(k);
+        if (it == label_pool.end()) it = label_pool.emplace(k, k).first;
+        return it->second.c_str();
+    }
     long long dev_bytes = 0;
     std::vector<void*> weight_allocs;
     std::unordered_map<const void*, size_t> weight_bytes;
@@ -317,6 +334,8 @@ int load_cnn(mrd_ctx* c, const Table& t, cudaStream_t s) {
             const std::string p(pre);
             if (!t.find(p + "conv1.weight")) break;
             if (c->blocks.size() <= bi) c->blocks.emplace_back();
+            if (c->block_stage.size() <= bi) c->block_stage.push_back(L);
+            c->block_stage[bi] = L;
             Bottleneck& b = c->blocks[bi++];
             const int stride = (i == 0 && L > 1) ? 2 : 1;
             MRD_TRY(load_conv_bn(c, t, p + "conv1", p + "bn1", 1, &b.c1, s));
@@ -697,15 +716,45 @@ int get_batch_plan(mrd_ctx* c, int B, BatchPlan** out) {
     return 0;
 }
 
-inline int run(mrd_ctx* c, const GemmLaunch& g, cudaStream_t s) {
-    ++c->launches;
+// ------------------------------------------------------------------ launch accounting / profiling
+// Every kernel launch of a forward goes through one ProfScope: it counts the launch and, when the
+// context is in profile mode (mrd_ctx_profile), brackets it with CUDA events on the launching stream
+// so bench.py can attribute device time, algorithmic FLOPs and bytes to each kernel family.
+enum Cat : int { CAT_TENSOR = 0, CAT_ATTN = 1, CAT_MEM = 2 };
+
+struct ProfScope {
+    mrd_ctx* c;
+    cudaStream_t s;
+    ProfRecord r;
+    ProfScope(mrd_ctx* c_, cudaStream_t s_, const char* label, int cat, double flops, double bytes)
+        : c(c_), s(s_) {
+        ++c->launches;
+        if (!c->profiling) return;
+        r.label = label;
+        r.cat = cat;
+        r.flops = flops;
+        r.bytes = bytes;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, s);
+    }
+    ~ProfScope() {
+        if (!c->profiling) return;
+        cudaEventRecord(r.e1, s);
+        c->prof.push_back(r);
+    }
+};
+
+inline int run(mrd_ctx* c, const char* label, const GemmLaunch& g, cudaStream_t s) {
+    ProfScope ps(c, s, label, CAT_TENSOR, g.flops, g.bytes);
     return launch_gemm(&g, s);
 }
-inline int run_f32(mrd_ctx* c, const GemmLaunch& g, float* out_f32, long long ld, cudaStream_t s) {
+inline int run_f32(mrd_ctx* c, const char* label, const GemmLaunch& g, float* out_f32, long long ld,
+                   cudaStream_t s) {
     GemmLaunch t = g;
     t.p.out_f32 = out_f32;
     t.p.ld_f32 = ld;
-    ++c->launches;
+    ProfScope ps(c, s, label, CAT_TENSOR, g.flops, g.bytes);
     return launch_gemm(&t, s);
 }
 
@@ -727,37 +776,50 @@ int run_backbone(mrd_ctx* c, const void* images, int img_dtype, int B, int H, in
     }
     MRD_TRY(ensure_cnn_ws(c, H, W));
     const size_t esz = img_dtype == MRD_DT_BF16 ? 2 : 4;
+    static const char* const kStage[5] = {"", "layer1", "layer2", "layer3", "layer4"};
     for (int b0 = 0; b0 < B; b0 += c->img_chunk) {
         const int nb = B - b0 < c->img_chunk ? B - b0 : c->img_chunk;
         CnnPlan* p;
         MRD_TRY(get_cnn_plan(c, nb, H, W, &p));
         const char* img = static_cast<const char*>(images) + static_cast<size_t>(b0) * 3 * H * W * esz;
-        MRD_TRY(repack_images(img, img_dtype == MRD_DT_BF16, nb, H, W, c->xpad, s));
-        MRD_TRY(run(c, p->stem, s));
-        MRD_TRY(maxpool3x3s2(c->stem_out, nb, H / 2, W / 2, 64, c->act0, s));
-        c->launches += 2;
-        for (auto& bp : p->blocks) {
-            MRD_TRY(run(c, bp.c1, s));
-            MRD_TRY(run(c, bp.c2, s));
-            if (bp.has_ds) MRD_TRY(run(c, bp.ds, s));
-            MRD_TRY(run(c, bp.c3, s));
+        {
+            ProfScope ps(c, s, "repack_images", CAT_MEM, 0,
+                         1.0 * nb * (3.0 * H * W * esz + (H + 6.0) * (W + 8) * 8));
+            MRD_TRY(repack_images(img, img_dtype == MRD_DT_BF16, nb, H, W, c->xpad, s));
         }
-        MRD_TRY(global_avgpool(p->final_act, nb, p->final_hw, c->feat_dim,
-                               c->b_pooled + 1LL * b0 * c->feat_dim,
-                               feat_pooled ? feat_pooled + 1LL * b0 * c->feat_dim : nullptr, s));
-        ++c->launches;
+        MRD_TRY(run(c, "conv_stem7x7", p->stem, s));
+        {
+            ProfScope ps(c, s, "maxpool3x3s2", CAT_MEM, 0, 1.0 * nb * (H / 2) * (W / 2) * 64 * 2 * 1.25);
+            MRD_TRY(maxpool3x3s2(c->stem_out, nb, H / 2, W / 2, 64, c->act0, s));
+        }
+        for (size_t i = 0; i < p->blocks.size(); ++i) {
+            auto& bp = p->blocks[i];
+            const char* st = kStage[c->block_stage[i]];
+            MRD_TRY(run(c, c->label(st, ".conv1_1x1"), bp.c1, s));
+            MRD_TRY(run(c, c->label(st, c->blocks[i].c2.stride == 2 ? ".conv2_3x3s2" : ".conv2_3x3"),
+                        bp.c2, s));
+            if (bp.has_ds) MRD_TRY(run(c, c->label(st, ".downsample"), bp.ds, s));
+            MRD_TRY(run(c, c->label(st, ".conv3_1x1+res"), bp.c3, s));
+        }
+        {
+            ProfScope ps(c, s, "global_avgpool", CAT_MEM, 0,
+                         1.0 * nb * c->feat_dim * (p->final_hw * 2.0 + 2.0));
+            MRD_TRY(global_avgpool(p->final_act, nb, p->final_hw, c->feat_dim,
+                                   c->b_pooled + 1LL * b0 * c->feat_dim,
+                                   feat_pooled ? feat_pooled + 1LL * b0 * c->feat_dim : nullptr, s));
+        }
         if (feat_map) {
+            ProfScope ps(c, s, "nhwc_to_nchw_f32", CAT_MEM, 0, 6.0 * nb * c->feat_dim * p->final_hw);
             MRD_TRY(nhwc_bf16_to_nchw_f32(p->final_act, nb, p->final_hw, c->feat_dim,
                                           feat_map + 1LL * b0 * c->feat_dim * p->final_hw, s));
-            ++c->launches;
         }
     }
     return 0;
 }
 
 int run_projection(mrd_ctx* c, BatchPlan* bp, float* emb_f32, cudaStream_t s) {
-    MRD_TRY(run(c, bp->proj1, s));
-    MRD_TRY(run_f32(c, bp->proj2, emb_f32, emb_f32 ? c->proj2.out : 0, s));
+    MRD_TRY(run(c, "cnn_proj1", bp->proj1, s));
+    MRD_TRY(run_f32(c, "cnn_proj2", bp->proj2, emb_f32, emb_f32 ? c->proj2.out : 0, s));
     return 0;
 }
 
@@ -785,23 +847,38 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
         MRD_TRY(get_text_plan(c, nb, S, &p));
         const void* m = mask ? static_cast<const char*>(mask) + static_cast<size_t>(b0) * S * msz[mask_dtype]
                              : nullptr;
-        MRD_TRY(mask_to_bias(m, mask_dtype, nb, S, c->t_bias, s));
-        MRD_TRY(bert_embed_layernorm(ids + 1LL * b0 * S, nb, S, c->word_emb, c->pos_type, c->emb_g,
-                                     c->emb_b, c->bert_ln_eps, c->vocab, c->t_h, s));
-        c->launches += 2;
+        {
+            ProfScope ps(c, s, "mask_to_bias", CAT_MEM, 0, 1.0 * T * (msz[mask_dtype] + 4));
+            MRD_TRY(mask_to_bias(m, mask_dtype, nb, S, c->t_bias, s));
+        }
+        {
+            ProfScope ps(c, s, "bert_embed_ln", CAT_MEM, 0, 1.0 * T * (8 + Hd * 2.0 * 2 + Hd * 4.0));
+            MRD_TRY(bert_embed_layernorm(ids + 1LL * b0 * S, nb, S, c->word_emb, c->pos_type, c->emb_g,
+                                         c->emb_b, c->bert_ln_eps, c->vocab, c->t_h, s));
+        }
+        const double ln_bytes = 1.0 * T * Hd * 2 * 2;
+        const double attn_flops = 4.0 * nb * c->bert_heads * S * 1.0 * S * 64;
         for (size_t i = 0; i < p->layers.size(); ++i) {
             const BertLayerW& L = c->layers[i];
             auto& lp = p->layers[i];
-            MRD_TRY(run(c, lp.qkv, s));
-            MRD_TRY(attention_forward(c->t_qkv, c->t_bias, nb, S, c->bert_heads, c->t_ctx, s));
-            MRD_TRY(run(c, lp.o, s));
-            MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b, c->bert_ln_eps, T,
-                                       Hd, c->t_h2, Hd, nullptr, 0, s));
-            MRD_TRY(run(c, lp.f1, s));
-            MRD_TRY(run(c, lp.f2, s));
-            MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
-                                       Hd, c->t_h, Hd, nullptr, 0, s));
-            c->launches += 3;
+            MRD_TRY(run(c, "bert.qkv", lp.qkv, s));
+            {
+                ProfScope ps(c, s, "bert.attention", CAT_ATTN, attn_flops, 1.0 * T * Hd * 2 * 4);
+                MRD_TRY(attention_forward(c->t_qkv, c->t_bias, nb, S, c->bert_heads, c->t_ctx, s));
+            }
+            MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
+            {
+                ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
+                MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b, c->bert_ln_eps, T,
+                                           Hd, c->t_h2, Hd, nullptr, 0, s));
+            }
+            MRD_TRY(run(c, "bert.ffn1+gelu", lp.f1, s));
+            MRD_TRY(run(c, "bert.ffn2+res", lp.f2, s));
+            {
+                ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
+                MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
+                                           Hd, c->t_h, Hd, nullptr, 0, s));
+            }
         }
         // CLS rows (src/text_encoder.py:118): token 0 of every sequence
         cudaError_t e = cudaMemcpy2DAsync(c->b_txt + 1LL * b0 * Hd, Hd * sizeof(bf16), c->t_h,
@@ -809,12 +886,12 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                                           cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync(CLS rows)");
         if (cls_f32) {
+            ProfScope ps(c, s, "cls_to_f32", CAT_MEM, 0, 6.0 * nb * Hd);
             MRD_TRY(cast_bf16_to_f32(c->t_h, 1LL * S * Hd, nb, Hd, cls_f32 + 1LL * b0 * Hd, Hd, s));
-            ++c->launches;
         }
         if (last_hidden) {
+            ProfScope ps(c, s, "hidden_to_f32", CAT_MEM, 0, 6.0 * T * Hd);
             MRD_TRY(cast_bf16_to_f32(c->t_h, Hd, T, Hd, last_hidden + 1LL * b0 * S * Hd, Hd, s));
-            ++c->launches;
         }
     }
     return 0;
@@ -823,25 +900,30 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
 int run_fusion(mrd_ctx* c, BatchPlan* bp, int B, float* fused_f32, float* attn_i2t, float* attn_t2i,
                cudaStream_t s) {
     const int F = c->fusion_dim;
-    MRD_TRY(run(c, bp->ip, s));
-    MRD_TRY(run(c, bp->tp, s));
-    MRD_TRY(run(c, bp->i2t, s));
-    MRD_TRY(run(c, bp->t2i, s));
-    MRD_TRY(layernorm_residual(c->b_prei, F, nullptr, 0, c->ln_i_g, c->ln_i_b, c->fusion_ln_eps, B, F,
-                               c->b_cat, 2 * F, nullptr, 0, s));
-    MRD_TRY(layernorm_residual(c->b_pret, F, nullptr, 0, c->ln_t_g, c->ln_t_b, c->fusion_ln_eps, B, F,
-                               c->b_cat + F, 2 * F, nullptr, 0, s));
-    c->launches += 2;
-    MRD_TRY(run(c, bp->f1, s));
-    MRD_TRY(run_f32(c, bp->f2, fused_f32, fused_f32 ? F : 0, s));
+    MRD_TRY(run(c, "fusion.image_proj", bp->ip, s));
+    MRD_TRY(run(c, "fusion.text_proj", bp->tp, s));
+    MRD_TRY(run(c, "fusion.img2txt_attn", bp->i2t, s));
+    MRD_TRY(run(c, "fusion.txt2img_attn", bp->t2i, s));
+    {
+        ProfScope ps(c, s, "fusion.layernorm", CAT_MEM, 0, 4.0 * B * F);
+        MRD_TRY(layernorm_residual(c->b_prei, F, nullptr, 0, c->ln_i_g, c->ln_i_b, c->fusion_ln_eps, B,
+                                   F, c->b_cat, 2 * F, nullptr, 0, s));
+    }
+    {
+        ProfScope ps(c, s, "fusion.layernorm", CAT_MEM, 0, 4.0 * B * F);
+        MRD_TRY(layernorm_residual(c->b_pret, F, nullptr, 0, c->ln_t_g, c->ln_t_b, c->fusion_ln_eps, B,
+                                   F, c->b_cat + F, 2 * F, nullptr, 0, s));
+    }
+    MRD_TRY(run(c, "fusion.mlp1", bp->f1, s));
+    MRD_TRY(run_f32(c, "fusion.mlp2", bp->f2, fused_f32, fused_f32 ? F : 0, s));
     // softmax over a single key: the weights are exactly 1 (src/fusion_model.py:138-164)
     if (attn_i2t) {
+        ProfScope ps(c, s, "fill_ones", CAT_MEM, 0, 4.0 * B * c->fusion_heads);
         MRD_TRY(fill_f32(attn_i2t, 1LL * B * c->fusion_heads, 1.0f, s));
-        ++c->launches;
     }
     if (attn_t2i) {
+        ProfScope ps(c, s, "fill_ones", CAT_MEM, 0, 4.0 * B * c->fusion_heads);
         MRD_TRY(fill_f32(attn_t2i, 1LL * B * c->fusion_heads, 1.0f, s));
-        ++c->launches;
     }
     return 0;
 }
@@ -850,13 +932,14 @@ int run_head(mrd_ctx* c, BatchPlan* bp, int B, float* logits, float* probs, cuda
     const bf16* x = c->b_fused;
     int ld = c->head_in;
     for (size_t j = 0; j < bp->head.size(); ++j) {
-        MRD_TRY(run(c, bp->head[j], s));
+        MRD_TRY(run(c, "head.hidden", bp->head[j], s));
         x = c->b_h[j & 1];
         ld = c->head_hidden[j].out;
     }
+    ProfScope ps(c, s, "head.logits_softmax", CAT_MEM, 0,
+                 1.0 * B * (c->head_last * 2.0 + c->num_classes * 8.0));
     MRD_TRY(head_logits_softmax(x, ld, c->head_out_w, c->head_out_b, B, c->head_last, c->num_classes,
                                 logits, probs, s));
-    ++c->launches;
     return 0;
 }
 
@@ -1014,11 +1097,16 @@ int mrd_fusion_fwd(mrd_ctx* c, const float* img_emb, const float* txt_emb, int B
     MRD_TRY(ensure_batch_ws(c, B));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
-    MRD_TRY(cast_f32_to_bf16(img_emb, c->fusion_img_in, B, c->fusion_img_in, c->b_img,
-                             c->fusion_img_in, s));
-    MRD_TRY(cast_f32_to_bf16(txt_emb, c->fusion_txt_in, B, c->fusion_txt_in, c->b_txt,
-                             c->fusion_txt_in, s));
-    c->launches += 2;
+    {
+        ProfScope ps(c, s, "cast_f32_to_bf16", CAT_MEM, 0, 6.0 * B * c->fusion_img_in);
+        MRD_TRY(cast_f32_to_bf16(img_emb, c->fusion_img_in, B, c->fusion_img_in, c->b_img,
+                                 c->fusion_img_in, s));
+    }
+    {
+        ProfScope ps(c, s, "cast_f32_to_bf16", CAT_MEM, 0, 6.0 * B * c->fusion_txt_in);
+        MRD_TRY(cast_f32_to_bf16(txt_emb, c->fusion_txt_in, B, c->fusion_txt_in, c->b_txt,
+                                 c->fusion_txt_in, s));
+    }
     return run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s);
 }
 
@@ -1033,8 +1121,10 @@ int mrd_head_fwd(mrd_ctx* c, const float* x, int B, float* logits, float* probs,
     MRD_TRY(ensure_batch_ws(c, B));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
-    MRD_TRY(cast_f32_to_bf16(x, c->head_in, B, c->head_in, c->b_fused, c->head_in, s));
-    ++c->launches;
+    {
+        ProfScope ps(c, s, "cast_f32_to_bf16", CAT_MEM, 0, 6.0 * B * c->head_in);
+        MRD_TRY(cast_f32_to_bf16(x, c->head_in, B, c->head_in, c->b_fused, c->head_in, s));
+    }
     return run_head(c, bp, B, logits, probs, s);
 }
 
@@ -1068,6 +1158,51 @@ int mrd_multimodal_fwd(mrd_ctx* c, const void* images, int img_dtype, const long
     MRD_TRY(run_bert(c, ids, mask, mask_dtype, B, S, txt_emb, nullptr, s));
     MRD_TRY(run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s));
     return run_head(c, bp, B, logits, probs, s);
+}
+
+int mrd_ctx_profile(mrd_ctx* c, int enable) {
+    MRD_TRY(check_ctx(c));
+    for (auto& r : c->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c->prof.clear();
+    c->profiling = enable != 0;
+    return 0;
+}
+
+int mrd_ctx_profile_report(mrd_ctx* c, char* buf, int cap) {
+    MRD_TRY(check_ctx(c));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cuda_fail(e, "mrd_ctx_profile_report: sync");
+    struct Agg {
+        int cat = 0;
+        long long n = 0;
+        double ms = 0, flops = 0, bytes = 0;
+    };
+    std::map<std::string, Agg> agg;
+    for (auto& r : c->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        Agg& a = agg[r.label];
+        a.cat = r.cat;
+        ++a.n;
+        a.ms += ms;
+        a.flops += r.flops;
+        a.bytes += r.bytes;
+    }
+    int off = 0;
+    for (auto& kv : agg) {
+        int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s,%d,%lld,%.6f,%.6e,%.6e\n",
+                         kv.first.c_str(), kv.second.cat, kv.second.n, kv.second.ms, kv.second.flops,
+                         kv.second.bytes);
+        if (w < 0 || off + w >= cap) {
+            set_last_error("mrd_ctx_profile_report: buffer too small");
+            return -1;
+        }
+        off += w;
+    }
+    return 0;
 }
 
 long long mrd_ctx_launch_count(const mrd_ctx* c) { return c ? c->launches : 0; }

@@ -386,6 +386,8 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     p.act = act;
     p.store_bf16 = Cout != nullptr;
     g->flops = 2.0 * M * static_cast<double>(N) * K;
+    g->bytes = 2.0 * (1.0 * M * K + 1.0 * N * K + (Cout ? 1.0 * M * N : 0.0) + (residual ? 1.0 * M * N : 0.0)) +
+               (out_f32 ? 4.0 * M * N : 0.0);
 
     const int bn = pick_block_n(N, p.tiles_w, gemm_num_sms());
     {
@@ -448,6 +450,8 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
     p.act = act;
     p.store_bf16 = 1;
     g->flops = 2.0 * N * Ho * Wo * static_cast<double>(Cout) * Cin * ksize * ksize;
+    g->bytes = 2.0 * (1.0 * N * H * W * Cin + 1.0 * Cout * Cin * ksize * ksize +
+                      1.0 * N * Ho * Wo * Cout * (residual ? 2.0 : 1.0));
 
     // tile box: as many whole output rows (then whole images) as fit in 128 GEMM rows
     p.tw = Wo < 128 ? Wo : 128;
@@ -540,6 +544,7 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
     p.act = act;
     p.store_bf16 = 1;
     g->flops = 2.0 * N * Ho * Wo * 64.0 * 147.0;
+    g->bytes = 2.0 * (1.0 * N * (H + 6) * (W + 8) * 4 + 64.0 * 7 * 32 + 1.0 * N * Ho * Wo * 64);
     p.tw = Wo >= 16 ? 16 : Wo;
     p.th = 128 / p.tw;
     if (p.th > Ho) p.th = Ho;

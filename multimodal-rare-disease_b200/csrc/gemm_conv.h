@@ -49,6 +49,7 @@ struct GemmLaunch {
     int stem;     // 1: 5-D overlapping-window A map, BLOCK_K = 32
     int grid;
     double flops;  // algorithmic FLOPs (2*M*N*K, un-padded), for reporting
+    double bytes;  // algorithmic bytes: A + W read once, C written once (+ residual read)
 };
 
 // Plain GEMM.  A: [M,K] bf16 with row stride lda; W: [N,K] bf16 (nn.Linear layout); C: [M,N] bf16

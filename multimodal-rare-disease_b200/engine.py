@@ -69,6 +69,22 @@ class Engine:
             _lib.check(self.lib.mrd_ctx_configure(self._ctx, int(img_chunk), int(seq_chunk_tokens)),
                        "mrd_ctx_configure")
 
+    def profile(self, enable: bool) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrd_ctx_profile(self._ctx, 1 if enable else 0), "mrd_ctx_profile")
+
+    def profile_report(self):
+        """[{label, cat, launches, ms, flops, bytes}] since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrd_ctx_profile_report(self._ctx, buf, len(buf)), "mrd_ctx_profile_report")
+        rows = []
+        for line in buf.value.decode().splitlines():
+            label, cat, n, ms, fl, by = line.split(",")
+            rows.append({"label": label, "cat": ("tensor", "attention", "memory")[int(cat)],
+                         "launches": int(n), "ms": float(ms), "flops": float(fl), "bytes": float(by)})
+        return rows
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mrd_ctx_launch_count(self._ctx))

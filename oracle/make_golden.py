@@ -73,7 +73,7 @@ def main():
     weights["sens"] = synth.sensitise(weights["plain"], 1)
     ref = build_reference()
     meta = {"checksum": {k: synth.checksum(v) for k, v in weights.items()},
-            "torch": torch.__version__}
+            "torch": str(torch.__version__)}
     torch.set_num_threads(os.cpu_count() or 1)
     with torch.no_grad():
         for name, (w, B, S, lengths, seed) in CASES.items():

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_parity_gpu.py -m gpu -q --timeout 600 2>&1 | tail -60 | tee gpurun_out/parity.log

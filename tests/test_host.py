@@ -1,0 +1,155 @@
+"""Host-side logic that needs no GPU: drop-in API surface, state_dict contract, loud failure without
+CUDA, shard arithmetic and the world_size-2 logits gather (gloo)."""
+
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mrd_b200
+import synth
+
+
+@pytest.fixture(scope="module")
+def model():
+    return synth.build_model(0)
+
+
+def test_state_dict_contract(model):
+    sd = model.state_dict()
+    assert len(sd) == 555  # SURVEY.md section 5 (PROBE on the reference)
+    assert sum(p.numel() for p in model.parameters()) == 136_842_698
+    for k in ("cnn_encoder.backbone.conv1.weight", "cnn_encoder.backbone.layer4.2.bn3.running_var",
+              "cnn_encoder.projection.0.weight", "cnn_encoder.projection.3.bias",
+              "text_encoder.encoder.embeddings.word_embeddings.weight",
+              "text_encoder.encoder.encoder.layer.11.output.LayerNorm.bias",
+              "text_encoder.encoder.pooler.dense.weight",
+              "fusion.fusion_layer.image_to_text_attention.query_proj.weight",
+              "fusion.fusion_layer.text_to_image_attention.output_proj.bias",
+              "fusion.fusion_layer.layer_norm_text.weight", "fusion.fusion_layer.fusion.3.weight",
+              "classifier.classifier.0.weight", "classifier.classifier.3.weight",
+              "classifier.classifier.6.bias"):
+        assert k in sd, k
+    assert sd["classifier.classifier.6.weight"].shape == (10, 128)
+    assert sd["fusion.fusion_layer.text_proj.weight"].shape == (512, 768)
+
+
+def test_module_tree_matches_reference_walks(model):
+    # the trainers walk these (src/train_multimodal.py:429-493); notebooks hook backbone.layer4
+    assert [n for n, _ in model.cnn_encoder.backbone.named_children()] == [
+        "conv1", "bn1", "relu", "maxpool", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc"]
+    assert len(model.text_encoder.encoder.encoder.layer) == 12
+    assert model.cnn_encoder.get_attention_layer() is model.cnn_encoder.backbone.layer4
+    assert model.num_classes == 10 and model.fusion_dim == 512
+    assert model.image_embedding_dim == 512 and model.text_embedding_dim == 768
+    # default config freezes the backbone (src/config.py:64) but not the projection
+    assert not any(p.requires_grad for p in model.cnn_encoder.backbone.parameters())
+    assert all(p.requires_grad for p in model.cnn_encoder.projection.parameters())
+    trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert trainable == 136_842_698 - 23_508_032
+
+
+def test_no_cpu_fallback(model):
+    x = torch.zeros(1, 3, 224, 224)
+    ids = torch.zeros(1, 8, dtype=torch.long)
+    with pytest.raises(mrd_b200.MrdError, match="CUDA devices only"):
+        model(x, ids, torch.ones_like(ids))
+    with pytest.raises(mrd_b200.MrdError):
+        model.cnn_encoder(x)
+    with pytest.raises(mrd_b200.MrdError):
+        model.text_encoder(ids, torch.ones_like(ids))
+    with pytest.raises(mrd_b200.MrdError):
+        model.fusion(torch.zeros(1, 512), torch.zeros(1, 768))
+    with pytest.raises(mrd_b200.MrdError):
+        model.classifier(torch.zeros(1, 512))
+
+
+def test_training_mode_is_refused_loudly(model):
+    model.train()
+    try:
+        with pytest.raises(NotImplementedError, match="eval"):
+            model(torch.zeros(1, 3, 224, 224), torch.zeros(1, 8, dtype=torch.long),
+                  torch.ones(1, 8, dtype=torch.long))
+    finally:
+        model.eval()
+
+
+def test_unsupported_configs_are_rejected():
+    with pytest.raises(ValueError, match="Unknown backbone"):
+        mrd_b200.CNNEncoder(mrd_b200.CNNEncoderConfig(backbone="vgg", pretrained=False))
+    with pytest.raises(NotImplementedError):
+        mrd_b200.CNNEncoder(mrd_b200.CNNEncoderConfig(backbone="efficientnet_b0", pretrained=False))
+    with pytest.raises(ValueError, match="Unknown fusion type"):
+        mrd_b200.MultimodalFusion(mrd_b200.FusionConfig(fusion_type="bilinear"))
+    with pytest.raises(NotImplementedError):
+        mrd_b200.MultimodalFusion(mrd_b200.FusionConfig(fusion_type="gated"))
+
+
+def test_freeze_helpers():
+    enc = mrd_b200.CNNEncoder(mrd_b200.CNNEncoderConfig(pretrained=False, freeze_backbone=False,
+                                                        freeze_layers=2))
+    frozen = {n.split(".")[0] for n, p in enc.backbone.named_parameters() if not p.requires_grad}
+    assert frozen == {"conv1", "bn1", "layer1", "layer2"}
+
+
+def test_deepcopy_and_pickle_drop_engine(model):
+    import copy
+    import pickle
+
+    m2 = copy.deepcopy(model.classifier)
+    assert "_mrd_engine" not in m2.__dict__
+    pickle.loads(pickle.dumps(model.classifier))
+
+
+def test_shard_bounds():
+    for total in (0, 1, 7, 16, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [mrd_b200.shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        mrd_b200.shard_bounds(4, 2, 2)
+
+
+def _dp_worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        images = torch.randn(total, 3, 4, 4, generator=g)
+        ids = torch.randint(0, 100, (total, 6), generator=g)
+        mask = torch.ones(total, 6, dtype=torch.long)
+
+        def local_forward(x, i, m, logits_out):  # stand-in for the CUDA forward: a per-sample function
+            logits_out.copy_(x.flatten(1)[:, :10] + i[:, :1].float() + m.sum(1, keepdim=True))
+
+        dp = mrd_b200.DataParallelForward(local_forward, 10)
+        got = dp.forward_global(images, ids, mask)
+        want = images.flatten(1)[:, :10] + ids[:, :1].float() + 6.0
+        lo, hi = mrd_b200.shard_bounds(total, world, rank)
+        got2 = dp.forward_shard(images[lo:hi], ids[lo:hi], mask[lo:hi], total)
+        q.put((rank, torch.equal(got, want), torch.equal(got2, want), tuple(got.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 7])
+def test_data_parallel_gather_world2(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + total
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ok1, ok2, shape in res:
+        assert ok1 and ok2 and shape == (total, 10), (rank, ok1, ok2, shape)
