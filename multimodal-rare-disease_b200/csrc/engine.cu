@@ -121,8 +121,8 @@ struct mrd_ctx {
     std::unordered_map<const void*, size_t> weight_bytes;
 
     // options
-    int img_chunk = 64;
-    int tok_chunk = 16384;
+    int img_chunk = 128;
+    int tok_chunk = 131072;
     int bert_heads = 12;
     float bert_ln_eps = 1e-12f;
     float bn_eps = 1e-5f;

@@ -4,8 +4,11 @@
 //                               (tap, 64-channel chunk)), B boxes from the [Cout][K] weight matrix
 //   warp 1      MMA issuer    : tcgen05.mma (128 x BLOCK_N x 16, bf16 -> fp32) into a double-buffered
 //                               TMEM accumulator; also owns the TMEM allocation
-//   warps 2..5  epilogue      : tcgen05.ld -> +bias (+residual) -> ReLU/GELU -> bf16 -> swizzled smem
-//                               -> TMA store (clipped by the tensor map), optional fp32 side output
+//   warps 2..9  epilogue      : per 64-column sub-tile: residual sub-tile prefetched by TMA into the
+//                               (swizzled) store staging buffer; tcgen05.ld -> +bias (+residual, in
+//                               place) -> ReLU/GELU -> bf16 -> staging -> TMA store (clipped by the
+//                               tensor map); optional fp32 side output.  8 warps: TMEM lane quarter =
+//                               warp % 4, two warps per quarter split the 64 columns.
 //
 // The epilogue of tile i overlaps the main loop of tile i+1 (two accumulator stages in TMEM).
 // Reference ops replaced: torchvision Bottleneck conv+bn+relu(+add) (TV:models/resnet.py:143-163),
@@ -27,9 +30,13 @@ namespace mrd {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;
-constexpr int kStageBufBytes = 128 * 128;  // one 128-row x 64-column bf16 store sub-tile
+constexpr int kNumThreads = 352;  // TMA warp + MMA warp + 8 epilogue warps + residual-loader warp
+constexpr int kEpiThreads = 256;
+constexpr int kStageBufBytes = 128 * 128;  // one 128-row x 64-column bf16 sub-tile (store / residual)
 constexpr int kSmemLimit = 232448;         // 227 KB opt-in limit per CTA
+constexpr int kMaxStages = 8;
+constexpr int kMaxRing = 8;
+constexpr int kBarBytes = 512;
 
 template <int BLOCK_N, bool STEM>
 struct Cfg {
@@ -37,10 +44,8 @@ struct Cfg {
     static constexpr int ROW_BYTES = BLOCK_K * 2;
     static constexpr int A_STAGE = kBlockM * ROW_BYTES;
     static constexpr int B_STAGE = BLOCK_N * ROW_BYTES;
-    static constexpr int FIXED = 2 * kStageBufBytes + BLOCK_N * 4 + 256 + 1024;  // staging+bias+bars+align
-    static constexpr int MAX_STAGES = (kSmemLimit - FIXED) / (A_STAGE + B_STAGE);
-    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
-    static constexpr int SMEM_BYTES = FIXED + STAGES * (A_STAGE + B_STAGE);
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    static constexpr int FIXED = 2 * kStageBufBytes + kBarBytes + 1024;  // staging + barriers + alignment
     static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
     static constexpr uint32_t LAYOUT = STEM ? 4u : 2u;  // SWIZZLE_64B : SWIZZLE_128B
     static constexpr uint32_t SBO = 8 * ROW_BYTES;      // 8-row core-matrix group pitch
@@ -64,11 +69,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
     return t;
 }
 
+// Shared-memory map (all offsets from a 1024-byte aligned base; stage / ring counts are runtime so
+// one binary serves the compute-bound GEMMs (deep operand pipeline, no residual ring) and the
+// memory-bound short-K convolutions with residual (shallow operand pipeline, deep residual ring)):
+//   [stages x A_STAGE][stages x B_STAGE][2 x 16 KB store staging][ring x 16 KB residual][barriers]
 template <int BLOCK_N, bool STEM>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BLOCK_N, STEM>;
-    constexpr int STAGES = C::STAGES;
+    const int STAGES = p.stages;
+    const int RING = p.ring;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -76,18 +86,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
     const uint32_t a_smem = smem_base;
     const uint32_t b_smem = a_smem + STAGES * C::A_STAGE;
-    const uint32_t st_smem = b_smem + STAGES * C::B_STAGE;  // 2 x 16 KB store staging (1024-aligned)
-    const uint32_t bias_smem = st_smem + 2 * kStageBufBytes;
-    const uint32_t bar_smem = bias_smem + BLOCK_N * 4;
-    float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_smem - smem_base));
+    const uint32_t st_smem = b_smem + STAGES * C::B_STAGE;
+    const uint32_t ring_smem = st_smem + 2 * kStageBufBytes;
+    const uint32_t bar_smem = ring_smem + RING * kStageBufBytes;
     uint8_t* st_gen = smem_gen + (st_smem - smem_base);
+    uint8_t* ring_gen = smem_gen + (ring_smem - smem_base);
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_smem - smem_base) + 192);
+        reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_smem - smem_base) + 320);
 
     auto full_bar = [&](int s) { return bar_smem + 8u * s; };
     auto empty_bar = [&](int s) { return bar_smem + 64u + 8u * s; };
-    auto tfull_bar = [&](int a) { return bar_smem + 128u + 8u * a; };
-    auto tempty_bar = [&](int a) { return bar_smem + 144u + 8u * a; };
+    auto rfull_bar = [&](int s) { return bar_smem + 128u + 8u * s; };
+    auto rempty_bar = [&](int s) { return bar_smem + 192u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_smem + 256u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_smem + 272u + 8u * a; };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -96,31 +108,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
         tma_prefetch_desc(&p.b_map);
         tma_prefetch_desc(&p.c_map);
-        for (int s = 0; s < STAGES; ++s) {
+        tma_prefetch_desc(&p.r_map);
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
+            mbar_init(rfull_bar(s), 1);
+            mbar_init(rempty_bar(s), 8);  // one arrival per epilogue warp
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 192);
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 320);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    constexpr int NSUB = BLOCK_N / 64;
     const int num_k = p.num_taps * p.kc_per_tap;
-    const uint32_t a_box_bytes = static_cast<uint32_t>(p.tw * p.th * p.nb) * C::ROW_BYTES;
+    const int box_rows = p.tw * p.th * p.nb;
+    const uint32_t a_box_bytes = static_cast<uint32_t>(box_rows) * C::ROW_BYTES;
     const uint32_t stage_tx = a_box_bytes + C::B_STAGE;
+    const int bid = static_cast<int>(blockIdx.x), nblk = static_cast<int>(gridDim.x);
+    const int my_tiles = (p.total_tiles - bid + nblk - 1) / nblk;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = bid; tile < p.total_tiles; tile += nblk) {
             const TileCoord t = decode_tile(p, tile);
             for (int ks = 0; ks < num_k; ++ks) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -150,7 +169,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = bid; tile < p.total_tiles; tile += nblk, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -177,111 +196,135 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
+    } else if (warp == 10) {
+        // ------------------------------------------------------------ residual loader
+        // Runs up to RING sub-tiles ahead of the epilogue so the residual (an HBM read the epilogue
+        // would otherwise wait ~2 us for) is already in shared memory when its sub-tile is due.
+        if (p.has_res) {
+            const uint32_t res_bytes = static_cast<uint32_t>(box_rows) * 128u;
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const TileCoord t = decode_tile(p, bid + it * nblk);
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    mbar_wait(rempty_bar(slot), phase ^ 1u);
+                    if (lane == 0) {
+                        mbar_expect_tx(rfull_bar(slot), res_bytes);
+                        tma_load_4d(&p.r_map, rfull_bar(slot), ring_smem + slot * kStageBufBytes,
+                                    t.n_idx * BLOCK_N + sub * 64, t.w0, t.h0, t.n0);
+                    }
+                    __syncwarp();
+                    if (++slot == RING) { slot = 0; phase ^= 1u; }
+                }
+            }
+        }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;   // accumulator row == smem staging row
-        const int epi_tid = threadIdx.x - 64;  // 0..127
-        const int box_rows = p.tw * p.th * p.nb;
+        // ------------------------------------------------------------ epilogue (warps 2..9)
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which 32 of the sub-tile's 64 columns
+        const int row = quarter * 32 + lane;    // accumulator row == smem staging row
+        const int epi_tid = threadIdx.x - 64;   // 0..255
         const int wi = row % p.tw;
         const int hi = (row / p.tw) % p.th;
         const int ni = row / (p.tw * p.th);
-        uint32_t sub_counter = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const TileCoord t = decode_tile(p, tile);
+        const bool has_res = p.has_res != 0;
+        const int nq = my_tiles * NSUB;  // sub-tiles this CTA produces
+        int rslot = 0;
+        uint32_t rphase = 0;
+
+        TileCoord t = decode_tile(p, bid);
+        for (int q = 0; q < nq; ++q) {
+            const int sub = q % NSUB;
+            const int it = q / NSUB;
             const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int col_base = t.n_idx * BLOCK_N;
+            const uint32_t buf = q & 1u;
+            if (sub == 0) t = decode_tile(p, bid + it * nblk);
+            const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;  // first global column of this thread
 
-            for (int i = epi_tid; i < BLOCK_N; i += 128)
-                bias_s[i] = p.bias ? __ldg(p.bias + col_base + i) : 0.0f;
-
-            const bool row_ok = (row < box_rows) && (t.n0 + ni < p.Nimg) && (t.h0 + hi < p.Ho) &&
-                                (t.w0 + wi < p.Wo);
-            const long long pix =
-                (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
-            const __nv_bfloat16* res_row =
-                (p.residual && row_ok) ? p.residual + pix * p.ld_res + col_base : nullptr;
-            float* f32_row = (p.out_f32 && row_ok) ? p.out_f32 + pix * p.ld_f32 + col_base : nullptr;
-
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-
-#pragma unroll 1
-            for (int sub = 0; sub < BLOCK_N / 64; ++sub, ++sub_counter) {
-                const uint32_t buf = sub_counter & 1u;
-                if (epi_tid == 0) tma_store_wait_read<1>();  // buffer `buf` (2 stores ago) drained
-                named_bar_sync(1, 128);
-                uint8_t* st_row = st_gen + buf * kStageBufBytes + row * 128;
+            if (sub == 0) {
+                mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
+                tc_fence_after();
+            }
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + sub * 64 +
+                          half * 32,
+                      v);
+            tmem_ld_wait();
+            if (sub == NSUB - 1) {
+                // accumulator stage fully read by this warp: hand it back to the MMA warp early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+            float f[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c0 = sub * 64 + half * 32;
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                  acc * BLOCK_N + c0,
-                              v);
-                    tmem_ld_wait();
-                    float f[32];
+            for (int j = 0; j < 32; j += 4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (has_res) {
+                mbar_wait(rfull_bar(rslot), rphase);
+                const uint8_t* r_row = ring_gen + rslot * kStageBufBytes + row * 128;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
-                        f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                        f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                        f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                        f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-                    }
-                    if (res_row) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 r4 =
-                                __ldg(reinterpret_cast<const uint4*>(res_row + c0) + q);
-                            const float2 r0 = unpack_bf16(r4.x), r1 = unpack_bf16(r4.y),
-                                         r2 = unpack_bf16(r4.z), r3 = unpack_bf16(r4.w);
-                            f[q * 8 + 0] += r0.x; f[q * 8 + 1] += r0.y;
-                            f[q * 8 + 2] += r1.x; f[q * 8 + 3] += r1.y;
-                            f[q * 8 + 4] += r2.x; f[q * 8 + 5] += r2.y;
-                            f[q * 8 + 6] += r3.x; f[q * 8 + 7] += r3.y;
-                        }
-                    }
-                    if (p.act == ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-                    } else if (p.act == ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    }
-                    if (f32_row) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(f32_row + c0 + j) =
-                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    // bf16 pack into the 128B-swizzled staging tile (matches the C tensor map)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 o;
-                        o.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
-                        o.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
-                        o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
-                        o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
-                        const int chunk = (half * 4 + q) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(st_row + chunk * 16) = o;
-                    }
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = (half * 4 + c) ^ (row & 7);
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(r_row + chunk * 16);
+                    const float2 r0 = unpack_bf16(r4.x), r1 = unpack_bf16(r4.y),
+                                 r2 = unpack_bf16(r4.z), r3 = unpack_bf16(r4.w);
+                    f[c * 8 + 0] += r0.x; f[c * 8 + 1] += r0.y;
+                    f[c * 8 + 2] += r1.x; f[c * 8 + 3] += r1.y;
+                    f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
+                    f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
                 }
-                if (sub == BLOCK_N / 64 - 1) {
-                    // accumulator fully read: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty_bar(rslot));
+                if (++rslot == RING) { rslot = 0; rphase ^= 1u; }
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+            }
+            if (p.out_f32) {
+                const bool row_ok = (row < box_rows) && (t.n0 + ni < p.Nimg) && (t.h0 + hi < p.Ho) &&
+                                    (t.w0 + wi < p.Wo);
+                if (row_ok) {
+                    const long long pix =
+                        (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
+                    float* f32_row = p.out_f32 + pix * p.ld_f32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(f32_row + j) =
+                            make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (epi_tid == 0 && p.store_bf16) {
-                    tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, col_base + sub * 64,
-                                 t.w0, t.h0, t.n0);
-                    tma_store_commit();
-                }
+            }
+            // staging buffer `buf` was the source of TMA store q-2: it must have been read out
+            if (epi_tid == 0) tma_store_wait_read<1>();
+            named_bar_sync(2, kEpiThreads);
+            // bf16 pack into the 128B-swizzled staging tile (matches the C tensor map)
+            uint8_t* st_row = st_gen + buf * kStageBufBytes + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16(f[c * 8 + 0], f[c * 8 + 1]);
+                o.y = pack_bf16(f[c * 8 + 2], f[c * 8 + 3]);
+                o.z = pack_bf16(f[c * 8 + 4], f[c * 8 + 5]);
+                o.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
+                const int chunk = (half * 4 + c) ^ (row & 7);
+                *reinterpret_cast<uint4*>(st_row + chunk * 16) = o;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (epi_tid == 0 && p.store_bf16) {
+                tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, t.n_idx * BLOCK_N + sub * 64,
+                             t.w0, t.h0, t.n0);
+                tma_store_commit();
             }
         }
         if (epi_tid == 0) tma_store_wait_all<0>();
@@ -302,15 +345,15 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
     auto kfn = conv_gemm_kernel<BLOCK_N, STEM>;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
-            set_last_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
-                           cudaGetErrorString(e));
+            set_last_error("cudaFuncSetAttribute(smem=%d): %s", kSmemLimit, cudaGetErrorString(e));
             return -static_cast<int>(e);
         }
         attr_set = true;
     }
-    kfn<<<g->grid, kNumThreads, C::SMEM_BYTES, stream>>>(g->p);
+    const int smem = C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
+    kfn<<<g->grid, kNumThreads, smem, stream>>>(g->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("conv_gemm_kernel<%d,%d> launch: %s", BLOCK_N, (int)STEM,
@@ -318,6 +361,32 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
         return -static_cast<int>(e);
     }
     return 0;
+}
+
+// Pipeline depths for one launch: operand stages vs residual ring (both live in the same 227 KB).
+void pick_pipeline(ConvGemmParams* p, int block_n, bool stem) {
+    const int stage = stem ? (128 * 64 + 64 * 64) : (128 * 128 + block_n * 128);
+    const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
+    const int avail = kSmemLimit - fixed;
+    const int num_k = p->num_taps * p->kc_per_tap;
+    if (!p->has_res) {
+        int s = avail / stage;
+        p->stages = s > kMaxStages ? kMaxStages : s;
+        p->ring = 0;
+        return;
+    }
+    // with a residual: short-K launches are memory-bound -> few operand stages (each already covers
+    // a whole tile), many residual sub-tiles in flight; long-K launches keep >= 3 operand stages
+    int s = num_k <= 2 ? 2 : 3;
+    while (s > 2 && (avail - s * stage) / kStageBufBytes < 2) --s;
+    int r = (avail - s * stage) / kStageBufBytes;
+    if (r > kMaxRing) {
+        r = kMaxRing;
+        int extra = (avail - r * kStageBufBytes) / stage;  // leftover smem back to the operand pipeline
+        if (extra > s) s = extra > kMaxStages ? kMaxStages : extra;
+    }
+    p->stages = s;
+    p->ring = r;
 }
 
 int pick_block_n(int n, long long m_tiles, int sms) {
@@ -340,6 +409,7 @@ int finish_plan(GemmLaunch* g, int block_n) {
         return -1;
     }
     p.total_tiles = static_cast<int>(total);
+    pick_pipeline(&p, block_n, g->stem != 0);
     const int sms = gemm_num_sms();
     g->grid = p.total_tiles < sms ? p.total_tiles : sms;
     return 0;
@@ -373,8 +443,7 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     ConvGemmParams& p = g->p;
     g->stem = 0;
     p.bias = bias;
-    p.residual = residual;
-    p.ld_res = ld_res;
+    p.has_res = residual != nullptr;
     p.out_f32 = out_f32;
     p.ld_f32 = ld_f32;
     p.num_taps = 1;
@@ -414,6 +483,19 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     } else {
         p.c_map = p.a_map[0];  // never dereferenced (store_bf16 == 0)
     }
+    if (residual) {
+        if (ld_res % 8 != 0) {
+            set_last_error("plan_gemm: residual row stride must be a multiple of 8 elements");
+            return -1;
+        }
+        uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
+        uint64_t str[3] = {(uint64_t)ld_res * 2, (uint64_t)ld_res * 2 * M, (uint64_t)ld_res * 2 * M};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_tensor_map(&p.r_map, residual, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    } else {
+        p.r_map = p.a_map[0];  // never dereferenced (has_res == 0)
+    }
     return finish_plan(g, bn);
 }
 
@@ -440,8 +522,7 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
     g->stem = 0;
     const int Ho = H / stride, Wo = W / stride;
     p.bias = bias;
-    p.residual = residual;
-    p.ld_res = Cout;
+    p.has_res = residual != nullptr;
     p.out_f32 = nullptr;
     p.ld_f32 = 0;
     p.num_taps = ksize * ksize;
@@ -520,6 +601,11 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
         uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
         int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
         if (rc) return rc;
+        p.r_map = p.c_map;
+        if (residual) {
+            rc = encode_tensor_map(&p.r_map, residual, 2, 4, dims, str, box, 128);
+            if (rc) return rc;
+        }
     }
     return finish_plan(g, bn);
 }
@@ -536,7 +622,7 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
     const int Ho = H / 2, Wo = W / 2;
     const int Hp = H + 6, Wp = W + 8;  // 3 rows/cols of zero padding before, 3/5 after
     p.bias = bias;
-    p.residual = nullptr;
+    p.has_res = 0;
     p.out_f32 = nullptr;
     p.num_taps = 7;
     p.kc_per_tap = 1;
@@ -575,6 +661,7 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
         uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
         int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
         if (rc) return rc;
+        p.r_map = p.c_map;
     }
     return finish_plan(g, 64);
 }

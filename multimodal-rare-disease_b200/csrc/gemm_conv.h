@@ -26,11 +26,12 @@ struct alignas(64) ConvGemmParams {
     CUtensorMap a_map[4];
     CUtensorMap b_map;
     CUtensorMap c_map;
+    CUtensorMap r_map;              // residual, same logical shape / boxes as the output
     const float* bias;              // [Cout] fp32
-    const __nv_bfloat16* residual;  // NHWC / row-major, same logical shape as the output, or null
     float* out_f32;                 // optional fp32 copy of the output, or null
-    long long ld_res;               // residual row (pixel) stride in elements
     long long ld_f32;               // out_f32 row stride in elements
+    int has_res;                    // 1: add the residual tile fetched through r_map
+    int stages, ring;               // operand pipeline depth, residual ring depth (16 KB sub-tiles)
     int num_taps;                   // 1, 7 (stem) or 9
     int kc_per_tap;                 // K chunks (of BLOCK_K) per tap
     TapDesc taps[9];
