@@ -167,6 +167,19 @@ int mrd_bert_embed_layernorm(const long long* ids, int B, int S, const void* wor
 int mrd_attention_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads, void* out,
                        void* stream);
 
+/* Token packing for BERT ("unpadding"): keeps token (b,j) iff mask[b,j] != 0 or j == 0 (or all tokens
+ * when keep_all).  Outputs (device): seq_off[B+1] first packed row of each sequence, row_tok[r] =
+ * b*S+j of packed row r, row_bias[r] = 0 / -inf key bias, n_rows[0] = number of packed rows.
+ * scratch: B ints.  Padded positions are masked as keys (HF:masking_utils.py:1001-1088) and only the
+ * CLS row is read downstream (src/text_encoder.py:118), so dropping them changes no output. */
+int mrd_compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_all, int* seq_off,
+                       int* row_tok, float* row_bias, int* n_rows, int* scratch, void* stream);
+
+/* mrd_attention_bf16 on the token-packed layout: sample b owns rows [seq_off[b], seq_off[b+1]) of qkv,
+ * row_bias and out; max_len bounds the sequence lengths. */
+int mrd_attention_varlen_bf16(const void* qkv, const float* row_bias, const int* seq_off, int B,
+                              int max_len, int heads, void* out, void* stream);
+
 /* attention_mask [B,S] -> additive key bias (0 / -inf). */
 int mrd_mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias, void* stream);
 

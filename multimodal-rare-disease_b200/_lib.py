@@ -55,6 +55,8 @@ SIGNATURES = {
     "mrd_bert_embed_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "mrd_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "mrd_mask_to_bias": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "mrd_compact_tokens": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mrd_attention_varlen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
 }
 
 

@@ -91,8 +91,25 @@ int mrd_bert_embed_layernorm(const long long* ids, int B, int S, const void* wor
 
 int mrd_attention_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads,
                        void* out, void* stream) {
-    return attention_forward(static_cast<const __nv_bfloat16*>(qkv), mask_bias, B, S, heads,
+    return attention_forward(static_cast<const __nv_bfloat16*>(qkv), mask_bias, nullptr, B, S, heads,
                              static_cast<__nv_bfloat16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int mrd_attention_varlen_bf16(const void* qkv, const float* row_bias, const int* seq_off, int B,
+                              int max_len, int heads, void* out, void* stream) {
+    if (!seq_off) {
+        set_last_error("mrd_attention_varlen_bf16: seq_off is required");
+        return -1;
+    }
+    return attention_forward(static_cast<const __nv_bfloat16*>(qkv), row_bias, seq_off, B, max_len,
+                             heads, static_cast<__nv_bfloat16*>(out),
+                             static_cast<cudaStream_t>(stream));
+}
+
+int mrd_compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_all, int* seq_off,
+                       int* row_tok, float* row_bias, int* n_rows, int* scratch, void* stream) {
+    return compact_tokens(mask, mask_dtype, B, S, keep_all, seq_off, row_tok, row_bias, n_rows,
+                          scratch, static_cast<cudaStream_t>(stream));
 }
 
 int mrd_mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias, void* stream) {

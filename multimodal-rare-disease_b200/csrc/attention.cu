@@ -72,10 +72,14 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* bas
     }
 }
 
+// seq_off == null: dense layout, sample b owns rows [b*S_max, (b+1)*S_max) and mask_bias is [B,S_max].
+// seq_off != null: token-packed layout, sample b owns rows [seq_off[b], seq_off[b+1]) and mask_bias is
+// indexed by packed row.
 template <int BLOCK_M>
-__global__ void __launch_bounds__(BLOCK_M * 2)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask_bias, int S,
-                 int heads, __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(BLOCK_M * 2, 2)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask_bias,
+                 const int* __restrict__ seq_off, int S_max, int heads,
+                 __nv_bfloat16* __restrict__ out) {
     constexpr int NT = BLOCK_M * 2;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t q_s = smem_u32(smem);
@@ -88,16 +92,25 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tq = lane & 3;
     const int q0 = blockIdx.x * BLOCK_M, h = blockIdx.y, b = blockIdx.z;
+    long long off;
+    int S;
+    if (seq_off) {
+        off = __ldg(seq_off + b);
+        S = __ldg(seq_off + b + 1) - static_cast<int>(off);
+    } else {
+        off = static_cast<long long>(b) * S_max;
+        S = S_max;
+    }
+    if (q0 >= S) return;  // uniform for the whole CTA
     const long long ld = 3LL * heads * kHeadDim;
-    const __nv_bfloat16* q_base = qkv + static_cast<long long>(b) * S * ld + h * kHeadDim;
+    const __nv_bfloat16* q_base = qkv + off * ld + h * kHeadDim;
     const __nv_bfloat16* k_base = q_base + heads * kHeadDim;
     const __nv_bfloat16* v_base = k_base + heads * kHeadDim;
 
     // ---- key bias -> smem, list of key blocks that contain at least one attended key
     const int nkb_total = (S + kBlockN - 1) / kBlockN;
     for (int i = tid; i < nkb_total * kBlockN; i += NT)
-        bias_s[i] = i < S ? (mask_bias ? __ldg(mask_bias + static_cast<long long>(b) * S + i) : 0.0f)
-                          : -INFINITY;
+        bias_s[i] = i < S ? (mask_bias ? __ldg(mask_bias + off + i) : 0.0f) : -INFINITY;
     __syncthreads();
     if (warp == 0) {
         int cnt = 0;
@@ -254,15 +267,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
         const int q = q0 + r;
         if (q < S) {
             const uint4 v = *reinterpret_cast<const uint4*>(q_gen + r * 128 + ((c ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * S + q) * ldo + h * kHeadDim +
-                                      c * 8) = v;
+            *reinterpret_cast<uint4*>(out + (off + q) * ldo + h * kHeadDim + c * 8) = v;
         }
     }
 }
 
 template <int BLOCK_M>
-int launch(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int heads,
-           __nv_bfloat16* out, cudaStream_t stream) {
+int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
+           int heads, __nv_bfloat16* out, cudaStream_t stream) {
     constexpr int SMEM = BLOCK_M * 128 + 4 * kBlockN * 128 + kMaxS * 4 + 64;
     static bool attr_set = false;
     auto kfn = attention_kernel<BLOCK_M>;
@@ -275,7 +287,7 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int h
         attr_set = true;
     }
     dim3 grid((S + BLOCK_M - 1) / BLOCK_M, heads, B);
-    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, S, heads, out);
+    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, seq_off, S, heads, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention_kernel<%d> launch: %s", BLOCK_M, cudaGetErrorString(e));
@@ -286,16 +298,19 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int h
 
 }  // namespace
 
-int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int heads,
-                      __nv_bfloat16* out, cudaStream_t stream) {
+int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
+                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream) {
     if (B <= 0 || S <= 0) return 0;
     if (S > kMaxS || heads <= 0 || heads > 65535 || B > 65535) {
         set_last_error("attention_forward: unsupported B=%d S=%d heads=%d (S <= %d)", B, S, heads,
                        kMaxS);
         return -1;
     }
-    if (S > 64) return launch<128>(qkv, mask_bias, B, S, heads, out, stream);
-    return launch<64>(qkv, mask_bias, B, S, heads, out, stream);
+    // 64-row query blocks when sequences are short (or packed to short lengths): a block whose rows
+    // all lie beyond the sequence exits immediately; 128-row blocks halve the K/V re-reads otherwise
+    if (S > 128 || (S > 64 && seq_off == nullptr))
+        return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
+    return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
 }
 
 }  // namespace mrd

@@ -10,7 +10,9 @@ namespace mrd {
 // mask_bias: [B,S] fp32 additive key bias (0 / -inf) or null; out: [B*S, heads*64] bf16.
 // Replaces BertSelfAttention's SDPA call (HF:models/bert/modeling_bert.py:168-207,
 // HF:integrations/sdpa_attention.py:92) without materialising the [B,1,S,S] mask.
-int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, int B, int S, int heads,
-                      __nv_bfloat16* out, cudaStream_t stream);
+// seq_off (optional, device, B+1 ints): token-packed layout - sample b owns rows
+// [seq_off[b], seq_off[b+1]) of qkv/out and of mask_bias; S is then the maximum sequence length.
+int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
+                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace mrd

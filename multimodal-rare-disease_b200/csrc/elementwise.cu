@@ -158,10 +158,11 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                  const __nv_bfloat16* __restrict__ res, long long ldr,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  int rows, __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ y32,
-                 long long ldy32) {
+                 long long ldy32, const int* __restrict__ dyn_rows) {
     constexpr int WIDTH = NCHUNK * 256;
     const int lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (dyn_rows) rows = min(rows, __ldg(dyn_rows));
     if (row >= rows) return;
     float v[NCHUNK][8];
     float sum = 0.0f;
@@ -218,11 +219,14 @@ __global__ void __launch_bounds__(256)
 bert_embed_ln_kernel(const long long* __restrict__ ids, int tokens, int S,
                      const __nv_bfloat16* __restrict__ word, const float* __restrict__ pos_type,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     int vocab, __nv_bfloat16* __restrict__ y) {
+                     int vocab, __nv_bfloat16* __restrict__ y, const int* __restrict__ row_tok,
+                     const int* __restrict__ dyn_rows) {
     constexpr int WIDTH = 768, NCHUNK = 3;
     const int lane = threadIdx.x & 31;
-    const long long tok = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tok >= tokens) return;
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (dyn_rows) tokens = min(tokens, __ldg(dyn_rows));
+    if (row >= tokens) return;
+    const long long tok = row_tok ? __ldg(row_tok + row) : row;
     long long id = __ldg(ids + tok);
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     const int pos = static_cast<int>(tok % S);
@@ -256,7 +260,119 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, int tokens, int S,
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             o[j] = (v[c][j] - mean) * rstd * __ldg(gamma + col + j) + __ldg(beta + col + j);
-        *reinterpret_cast<uint4*>(y + tok * WIDTH + col) = pack8(o);
+        *reinterpret_cast<uint4*>(y + row * WIDTH + col) = pack8(o);
+    }
+}
+
+// ------------------------------------------------------------------ token packing
+__device__ __forceinline__ bool mask_nonzero(const void* mask, int dtype, long long i) {
+    switch (dtype) {
+        case MRD_DT_I64: return static_cast<const long long*>(mask)[i] != 0;
+        case MRD_DT_I32: return static_cast<const int*>(mask)[i] != 0;
+        case MRD_DT_F32: return static_cast<const float*>(mask)[i] != 0.0f;
+        case MRD_DT_BF16: return __bfloat162float(static_cast<const __nv_bfloat16*>(mask)[i]) != 0.0f;
+        default: return static_cast<const unsigned char*>(mask)[i] != 0;
+    }
+}
+
+// one warp per sequence: number of kept tokens
+__global__ void compact_count_kernel(const void* __restrict__ mask, int dtype, int B, int S,
+                                     int keep_all, int* __restrict__ counts) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int n = 0;
+    if (keep_all || mask == nullptr) {
+        n = S;
+    } else {
+        for (int j0 = 0; j0 < S; j0 += 32) {
+            const int j = j0 + lane;
+            const bool keep = j < S && (j == 0 || mask_nonzero(mask, dtype, static_cast<long long>(b) * S + j));
+            n += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+    }
+    if (lane == 0) counts[b] = n;
+}
+
+// single block: exclusive scan of counts -> seq_off[0..B], n_rows
+__global__ void compact_scan_kernel(const int* __restrict__ counts, int B, int* __restrict__ seq_off,
+                                    int* __restrict__ n_rows) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < B ? counts[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_tot[lane] = w;  // inclusive totals per warp
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int incl = x + (warp > 0 ? warp_tot[warp - 1] : 0) + carry;
+        if (i < B) seq_off[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        seq_off[B] = carry_s;
+        n_rows[0] = carry_s;
+    }
+}
+
+// one warp per sequence: packed row -> token index and key bias
+__global__ void compact_fill_kernel(const void* __restrict__ mask, int dtype, int B, int S,
+                                    int keep_all, const int* __restrict__ seq_off,
+                                    int* __restrict__ row_tok, float* __restrict__ row_bias) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int r = seq_off[b];
+    for (int j0 = 0; j0 < S; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = j < S && (mask == nullptr || mask_nonzero(mask, dtype, static_cast<long long>(b) * S + j));
+        const bool keep = j < S && (keep_all || mask == nullptr || valid || j == 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int dst = r + __popc(bal & ((1u << lane) - 1u));
+            row_tok[dst] = b * S + j;
+            row_bias[dst] = valid ? 0.0f : -INFINITY;
+        }
+        r += __popc(bal);
+    }
+}
+
+__global__ void gather_cls_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ seq_off,
+                                  int B, int width8, uint4* __restrict__ y_bf16,
+                                  float* __restrict__ y_f32) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * width8) return;
+    const int c = static_cast<int>(i % width8);
+    const int b = static_cast<int>(i / width8);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(seq_off[b]) * width8 * 8) + c);
+    if (y_bf16) y_bf16[i] = v;
+    if (y_f32) {
+        float f[8];
+        unpack8(v, f);
+        float4* o = reinterpret_cast<float4*>(y_f32 + i * 8);
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
     }
 }
 
@@ -482,7 +598,7 @@ int global_avgpool(const __nv_bfloat16* x, int N, int HW, int C, __nv_bfloat16* 
 int layernorm_residual(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* residual,
                        long long ldr, const float* gamma, const float* beta, float eps, int rows,
                        int width, __nv_bfloat16* y_bf16, long long ldy, float* y_f32,
-                       long long ldy32, cudaStream_t s) {
+                       long long ldy32, cudaStream_t s, const int* dyn_rows) {
     if (rows <= 0) return 0;
     if (ldx % 8 != 0 || (residual && ldr % 8 != 0) || (y_bf16 && ldy % 8 != 0) ||
         (y_f32 && ldy32 % 4 != 0)) {
@@ -492,7 +608,7 @@ int layernorm_residual(const __nv_bfloat16* x, long long ldx, const __nv_bfloat1
     const unsigned grid = blocks_for(rows, 8);
 #define MRD_LN(NC)                                                                              \
     layernorm_kernel<NC><<<grid, 256, 0, s>>>(x, ldx, residual, ldr, gamma, beta, eps, rows,    \
-                                              y_bf16, ldy, y_f32, ldy32)
+                                              y_bf16, ldy, y_f32, ldy32, dyn_rows)
     switch (width) {
         case 256: MRD_LN(1); break;
         case 512: MRD_LN(2); break;
@@ -508,12 +624,41 @@ int layernorm_residual(const __nv_bfloat16* x, long long ldx, const __nv_bfloat1
 
 int bert_embed_layernorm(const long long* ids, int B, int S, const __nv_bfloat16* word_emb,
                          const float* pos_type_emb, const float* gamma, const float* beta,
-                         float eps, int vocab, __nv_bfloat16* y, cudaStream_t s) {
+                         float eps, int vocab, __nv_bfloat16* y, cudaStream_t s, const int* row_tok,
+                         const int* dyn_rows) {
     const long long tokens = static_cast<long long>(B) * S;
     if (tokens <= 0) return 0;
     bert_embed_ln_kernel<<<blocks_for(tokens, 8), 256, 0, s>>>(
-        ids, static_cast<int>(tokens), S, word_emb, pos_type_emb, gamma, beta, eps, vocab, y);
+        ids, static_cast<int>(tokens), S, word_emb, pos_type_emb, gamma, beta, eps, vocab, y, row_tok,
+        dyn_rows);
     return check_launch("bert_embed_layernorm");
+}
+
+int compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_all, int* seq_off,
+                   int* row_tok, float* row_bias, int* n_rows, int* scratch, cudaStream_t s) {
+    if (B <= 0 || S <= 0) return 0;
+    if (mask && (mask_dtype < MRD_DT_I64 || mask_dtype > MRD_DT_BF16)) {
+        set_last_error("compact_tokens: unknown mask dtype code %d", mask_dtype);
+        return -1;
+    }
+    compact_count_kernel<<<blocks_for(B, 8), 256, 0, s>>>(mask, mask_dtype, B, S, keep_all, scratch);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(scratch, B, seq_off, n_rows);
+    compact_fill_kernel<<<blocks_for(B, 8), 256, 0, s>>>(mask, mask_dtype, B, S, keep_all, seq_off,
+                                                        row_tok, row_bias);
+    return check_launch("compact_tokens");
+}
+
+int gather_cls_rows(const __nv_bfloat16* x, const int* seq_off, int B, int width,
+                    __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t s) {
+    if (B <= 0) return 0;
+    if (width % 8 != 0) {
+        set_last_error("gather_cls_rows: width %% 8 != 0");
+        return -1;
+    }
+    const long long total = static_cast<long long>(B) * (width / 8);
+    gather_cls_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, seq_off, B, width / 8,
+                                                           reinterpret_cast<uint4*>(y_bf16), y_f32);
+    return check_launch("gather_cls_rows");
 }
 
 int mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias, cudaStream_t s) {

@@ -24,15 +24,33 @@ int global_avgpool(const __nv_bfloat16* x, int N, int HW, int C, __nv_bfloat16* 
 // y = LayerNorm(x + residual) * gamma + beta, one warp per row, fp32 statistics
 // (HF:models/bert/modeling_bert.py:294-298,352-356; src/fusion_model.py:274-276).
 // width in {256,512,768,1024}; residual may be null; either output may be null.
+// dyn_rows (optional, device): the number of rows actually processed, <= rows (token-packed BERT).
 int layernorm_residual(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* residual,
                        long long ldr, const float* gamma, const float* beta, float eps, int rows,
                        int width, __nv_bfloat16* y_bf16, long long ldy, float* y_f32,
-                       long long ldy32, cudaStream_t s);
+                       long long ldy32, cudaStream_t s, const int* dyn_rows = nullptr);
 
 // word[ids] + (position + token_type[0]) -> LayerNorm (HF:models/bert/modeling_bert.py:72-112).
+// row_tok / dyn_rows (optional, device): packed row r embeds token row_tok[r] (= b*S + j) and only
+// *dyn_rows rows exist; without them row r is token r.
 int bert_embed_layernorm(const long long* ids, int B, int S, const __nv_bfloat16* word_emb,
                          const float* pos_type_emb, const float* gamma, const float* beta,
-                         float eps, int vocab, __nv_bfloat16* y, cudaStream_t s);
+                         float eps, int vocab, __nv_bfloat16* y, cudaStream_t s,
+                         const int* row_tok = nullptr, const int* dyn_rows = nullptr);
+
+// Token packing ("unpadding") for BERT: keeps token (b,j) iff mask[b,j] != 0 or j == 0 (the CLS row
+// is always needed, src/text_encoder.py:118) - or every token when keep_all.  Padded positions never
+// influence attended ones (HF:masking_utils.py:1001-1088 masks them as keys) and only the CLS row is
+// read downstream, so dropping them changes no output of TextEncoder.forward.
+//   seq_off[B+1]: first packed row of each sequence; row_tok[r]: b*S + j of packed row r;
+//   row_bias[r]: 0 / -inf additive key bias of packed row r; n_rows[0] = seq_off[B].
+// scratch: B ints.  mask may be null (all ones).
+int compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_all, int* seq_off,
+                   int* row_tok, float* row_bias, int* n_rows, int* scratch, cudaStream_t s);
+
+// CLS rows of a packed hidden state: row seq_off[b] of x -> y_bf16[b], y_f32[b] (either optional).
+int gather_cls_rows(const __nv_bfloat16* x, const int* seq_off, int B, int width,
+                    __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t s);
 
 // attention_mask [B,S] (MRD_DT_* code) -> additive key bias (0 or -inf), the key-padding semantics
 // of HF:masking_utils.py:1001-1088.

@@ -168,7 +168,8 @@ struct mrd_ctx {
     // text chunk buffers
     bf16 *t_h = nullptr, *t_h2 = nullptr, *t_qkv = nullptr, *t_ctx = nullptr, *t_tmp = nullptr,
          *t_ffn = nullptr;
-    float* t_bias = nullptr;
+    float* t_bias = nullptr;   // key bias per packed row
+    int *t_seq_off = nullptr, *t_row_tok = nullptr, *t_nrows = nullptr, *t_scratch = nullptr;
     // batch buffers
     bf16 *b_pooled = nullptr, *b_projh = nullptr, *b_img = nullptr, *b_txt = nullptr, *b_ip = nullptr,
          *b_tp = nullptr, *b_prei = nullptr, *b_pret = nullptr, *b_cat = nullptr, *b_fh = nullptr,
@@ -579,7 +580,8 @@ int ensure_text_ws(mrd_ctx* c, int tokens) {
     c->text_plans.clear();
     const long long T = tokens;
     const int Hd = c->hidden;
-    size_t total = 4 * pad1k(T * Hd, 2) + pad1k(T * 3 * Hd, 2) + pad1k(T * c->ffn, 2) + pad1k(T, 4);
+    size_t total = 4 * pad1k(T * Hd, 2) + pad1k(T * 3 * Hd, 2) + pad1k(T * c->ffn, 2) +
+                   4 * pad1k(T + 2, 4) + pad1k(1, 4);
     MRD_TRY(arena_reset(c, &c->text_ws, total));
     c->t_h = arena_take<bf16>(&c->text_ws, T * Hd);
     c->t_h2 = arena_take<bf16>(&c->text_ws, T * Hd);
@@ -587,7 +589,11 @@ int ensure_text_ws(mrd_ctx* c, int tokens) {
     c->t_tmp = arena_take<bf16>(&c->text_ws, T * Hd);
     c->t_qkv = arena_take<bf16>(&c->text_ws, T * 3 * Hd);
     c->t_ffn = arena_take<bf16>(&c->text_ws, T * c->ffn);
-    c->t_bias = arena_take<float>(&c->text_ws, T);
+    c->t_bias = arena_take<float>(&c->text_ws, T + 2);
+    c->t_seq_off = arena_take<int>(&c->text_ws, T + 2);
+    c->t_row_tok = arena_take<int>(&c->text_ws, T + 2);
+    c->t_scratch = arena_take<int>(&c->text_ws, T + 2);
+    c->t_nrows = arena_take<int>(&c->text_ws, 1);
     c->text_ws_tokens = tokens;
     return 0;
 }
@@ -614,6 +620,8 @@ int get_text_plan(mrd_ctx* c, int B, int S, TextPlan** out) {
                           nullptr, 0, nullptr, 0, ACT_GELU));
         MRD_TRY(plan_gemm(&lp.f2, c->t_ffn, c->ffn, T, c->ffn, L.f2.w, Hd, L.f2.b, c->t_tmp, Hd,
                           c->t_h2, Hd, nullptr, 0, ACT_NONE));
+        // rows are token-packed: the live count is produced on the device by compact_tokens
+        lp.qkv.p.dyn_rows = lp.o.p.dyn_rows = lp.f1.p.dyn_rows = lp.f2.p.dyn_rows = c->t_nrows;
     }
     auto ins = c->text_plans.emplace(key, std::move(p));
     *out = &ins.first->second;
@@ -847,14 +855,20 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
         MRD_TRY(get_text_plan(c, nb, S, &p));
         const void* m = mask ? static_cast<const char*>(mask) + static_cast<size_t>(b0) * S * msz[mask_dtype]
                              : nullptr;
+        // token packing: padded positions are dropped (they influence nothing TextEncoder.forward
+        // returns); every later kernel reads the live row count from the device, so no host sync
+        const int keep_all = last_hidden != nullptr;
         {
-            ProfScope ps(c, s, "mask_to_bias", CAT_MEM, 0, 1.0 * T * (msz[mask_dtype] + 4));
-            MRD_TRY(mask_to_bias(m, mask_dtype, nb, S, c->t_bias, s));
+            ProfScope ps(c, s, "compact_tokens", CAT_MEM, 0, 1.0 * T * (msz[mask_dtype] + 8));
+            MRD_TRY(compact_tokens(m, mask_dtype, nb, S, keep_all, c->t_seq_off, c->t_row_tok,
+                                   c->t_bias, c->t_nrows, c->t_scratch, s));
+            c->launches += 2;
         }
         {
             ProfScope ps(c, s, "bert_embed_ln", CAT_MEM, 0, 1.0 * T * (8 + Hd * 2.0 * 2 + Hd * 4.0));
             MRD_TRY(bert_embed_layernorm(ids + 1LL * b0 * S, nb, S, c->word_emb, c->pos_type, c->emb_g,
-                                         c->emb_b, c->bert_ln_eps, c->vocab, c->t_h, s));
+                                         c->emb_b, c->bert_ln_eps, c->vocab, c->t_h, s, c->t_row_tok,
+                                         c->t_nrows));
         }
         const double ln_bytes = 1.0 * T * Hd * 2 * 2;
         const double attn_flops = 4.0 * nb * c->bert_heads * S * 1.0 * S * 64;
@@ -864,32 +878,30 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
             MRD_TRY(run(c, "bert.qkv", lp.qkv, s));
             {
                 ProfScope ps(c, s, "bert.attention", CAT_ATTN, attn_flops, 1.0 * T * Hd * 2 * 4);
-                MRD_TRY(attention_forward(c->t_qkv, c->t_bias, nb, S, c->bert_heads, c->t_ctx, s));
+                MRD_TRY(attention_forward(c->t_qkv, c->t_bias, c->t_seq_off, nb, S, c->bert_heads,
+                                          c->t_ctx, s));
             }
             MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
             {
                 ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
                 MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b, c->bert_ln_eps, T,
-                                           Hd, c->t_h2, Hd, nullptr, 0, s));
+                                           Hd, c->t_h2, Hd, nullptr, 0, s, c->t_nrows));
             }
             MRD_TRY(run(c, "bert.ffn1+gelu", lp.f1, s));
             MRD_TRY(run(c, "bert.ffn2+res", lp.f2, s));
             {
                 ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
                 MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
-                                           Hd, c->t_h, Hd, nullptr, 0, s));
+                                           Hd, c->t_h, Hd, nullptr, 0, s, c->t_nrows));
             }
         }
-        // CLS rows (src/text_encoder.py:118): token 0 of every sequence
-        cudaError_t e = cudaMemcpy2DAsync(c->b_txt + 1LL * b0 * Hd, Hd * sizeof(bf16), c->t_h,
-                                          1LL * S * Hd * sizeof(bf16), Hd * sizeof(bf16), nb,
-                                          cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync(CLS rows)");
-        if (cls_f32) {
-            ProfScope ps(c, s, "cls_to_f32", CAT_MEM, 0, 6.0 * nb * Hd);
-            MRD_TRY(cast_bf16_to_f32(c->t_h, 1LL * S * Hd, nb, Hd, cls_f32 + 1LL * b0 * Hd, Hd, s));
+        // CLS rows (src/text_encoder.py:118): the first packed row of every sequence
+        {
+            ProfScope ps(c, s, "gather_cls", CAT_MEM, 0, 8.0 * nb * Hd);
+            MRD_TRY(gather_cls_rows(c->t_h, c->t_seq_off, nb, Hd, c->b_txt + 1LL * b0 * Hd,
+                                    cls_f32 ? cls_f32 + 1LL * b0 * Hd : nullptr, s));
         }
-        if (last_hidden) {
+        if (last_hidden) {  // keep_all: packed layout == dense [nb,S,Hd]
             ProfScope ps(c, s, "hidden_to_f32", CAT_MEM, 0, 6.0 * T * Hd);
             MRD_TRY(cast_bf16_to_f32(c->t_h, Hd, T, Hd, last_hidden + 1LL * b0 * S * Hd, Hd, s));
         }

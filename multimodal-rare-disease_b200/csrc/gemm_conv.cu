@@ -133,13 +133,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t a_box_bytes = static_cast<uint32_t>(box_rows) * C::ROW_BYTES;
     const uint32_t stage_tx = a_box_bytes + C::B_STAGE;
     const int bid = static_cast<int>(blockIdx.x), nblk = static_cast<int>(gridDim.x);
-    const int my_tiles = (p.total_tiles - bid + nblk - 1) / nblk;
+    // token-packed BERT: the live row count is only known on the device
+    int total_tiles = p.total_tiles;
+    if (p.dyn_rows) {
+        const int live = (__ldg(p.dyn_rows) + kBlockM - 1) / kBlockM * p.n_tiles_n;
+        total_tiles = live < total_tiles ? live : total_tiles;
+    }
+    const int my_tiles = total_tiles > bid ? (total_tiles - bid + nblk - 1) / nblk : 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = bid; tile < p.total_tiles; tile += nblk) {
+        for (int tile = bid; tile < total_tiles; tile += nblk) {
             const TileCoord t = decode_tile(p, tile);
             for (int ks = 0; ks < num_k; ++ks) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -169,7 +175,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = bid; tile < p.total_tiles; tile += nblk, ++it) {
+        for (int tile = bid; tile < total_tiles; tile += nblk, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);

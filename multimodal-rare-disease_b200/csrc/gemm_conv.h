@@ -30,6 +30,7 @@ struct alignas(64) ConvGemmParams {
     const float* bias;              // [Cout] fp32
     float* out_f32;                 // optional fp32 copy of the output, or null
     long long ld_f32;               // out_f32 row stride in elements
+    const int* dyn_rows;            // optional (device): live GEMM rows <= M; tiles beyond are skipped
     int has_res;                    // 1: add the residual tile fetched through r_map
     int stages, ring;               // operand pipeline depth, residual ring depth (16 KB sub-tiles)
     int num_taps;                   // 1, 7 (stem) or 9

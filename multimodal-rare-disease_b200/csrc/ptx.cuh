@@ -211,19 +211,25 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
-// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16
-// rounding of the result) on the fast-math units: one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner
-// chain, so the epilogue keeps pace with the tensor core (erff() costs ~3x as many issue slots).
+// Exact-erf GELU (HF:activations.py:70-90) with erf from Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the bf16 rounding of the result), written against the raw fast-math
+// units: one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner chain = 16 issue slots per element, so the
+// FFN1 epilogue keeps pace with the tensor core (erff(), or __fdividef/__expf with their range
+// fix-ups, cost 2-3x as many).
+//   z = |x|/sqrt(2), t = 1/(1 + p z), h = 0.5 (a1 t + ... + a5 t^5) exp(-z^2) = 0.5 erfc(z)
+//   gelu(x) = x * (x >= 0 ? 1 - h : h)
 __device__ __forceinline__ float gelu_erf_fast(float x) {
+    float t, e;
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = poly * t * __expf(-z * z);  // 1 - erf(z)
-    const float erf_abs = 1.0f - e;
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    // exp(-z^2) = 2^(-x^2 * 0.5 * log2(e))
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float h = poly * t * e;
+    return x * (x >= 0.0f ? 1.0f - h : h);
 }
 
 }  // namespace mrd

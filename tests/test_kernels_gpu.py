@@ -259,3 +259,59 @@ def test_mask_dtypes(lib, cuda, dtype, code):
     _check(lib, lib.mrd_mask_to_bias(mm.data_ptr(), code, 3, 77, bias.data_ptr(), _stream()))
     torch.cuda.synchronize()
     assert torch.equal(bias == 0, m)
+
+
+# ------------------------------------------------------------------ token packing + varlen attention
+@pytest.mark.parametrize("B,S,keep_all", [(7, 128, 0), (3, 40, 0), (4, 33, 1), (1500, 16, 0)])
+def test_compact_tokens(lib, cuda, B, S, keep_all):
+    g = torch.Generator(device="cuda").manual_seed(B)
+    mask = (torch.rand(B, S, device=cuda, generator=g) > 0.45).long()   # arbitrary holes, not only prefixes
+    mask[0] = 1
+    if B > 1:
+        mask[1] = 0                                                       # fully masked row: CLS still kept
+    seq_off = torch.full((B + 1,), -1, device=cuda, dtype=torch.int32)
+    row_tok = torch.full((B * S,), -1, device=cuda, dtype=torch.int32)
+    row_bias = torch.full((B * S,), 7.0, device=cuda)
+    n_rows = torch.zeros(1, device=cuda, dtype=torch.int32)
+    scratch = torch.zeros(B, device=cuda, dtype=torch.int32)
+    _check(lib, lib.mrd_compact_tokens(mask.data_ptr(), 0, B, S, keep_all, seq_off.data_ptr(),
+                                       row_tok.data_ptr(), row_bias.data_ptr(), n_rows.data_ptr(),
+                                       scratch.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    keep = mask.bool().clone()
+    keep[:, 0] = True
+    if keep_all:
+        keep[:] = True
+    counts = keep.sum(1)
+    want_off = torch.cat([torch.zeros(1, device=cuda, dtype=torch.long), counts.cumsum(0)])
+    assert torch.equal(seq_off.long(), want_off)
+    n = int(n_rows.item())
+    assert n == int(counts.sum())
+    want_tok = keep.flatten().nonzero().flatten()
+    assert torch.equal(row_tok[:n].long(), want_tok)
+    want_bias = torch.where(mask.flatten()[want_tok] != 0, 0.0, float("-inf"))
+    assert torch.equal(row_bias[:n], want_bias.float())
+
+
+@pytest.mark.parametrize("lens,heads", [([128, 70, 1, 64, 65], 12), ([512, 64, 300], 12), ([5, 48, 33], 4)])
+def test_attention_varlen(lib, cuda, lens, heads):
+    g = torch.Generator(device="cuda").manual_seed(sum(lens))
+    B, D, T = len(lens), heads * 64, sum(lens)
+    qkv = torch.randn(T, 3 * D, device=cuda, generator=g).to(BF)
+    qkv[:, :D] *= 0.125
+    seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=cuda, dtype=torch.int32)
+    bias = torch.zeros(T, device=cuda)
+    bias[seq_off[1].item()] = float("-inf")   # a kept-but-masked CLS row (sample 1)
+    out = torch.full((T, D), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_attention_varlen_bf16(qkv.data_ptr(), bias.data_ptr(), seq_off.data_ptr(), B,
+                                              max(lens), heads, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    for b, L in enumerate(lens):
+        o = int(seq_off[b])
+        x = qkv[o:o + L].float()
+        q, k, v = [t.view(L, heads, 64).transpose(0, 1) for t in x.split(D, -1)]
+        sc = q @ k.transpose(-1, -2) + bias[o:o + L].view(1, 1, L)
+        if L == 1 and torch.isinf(bias[o]):
+            continue  # every key masked: the reference yields NaN, this path yields zeros
+        ref = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(L, D)
+        _close(out[o:o + L], ref, rel=2 ** -6, abs_=2e-2, what=f"varlen attention sample {b}")
