@@ -125,6 +125,65 @@ class MultimodalClassifier(B200Module):
             confidence, predicted = torch.max(probs, dim=-1)
         return predicted, confidence
 
+    def forward_host(self, images: torch.Tensor, input_ids: torch.Tensor,
+                     attention_mask: Optional[torch.Tensor], micro_batch: int = 512, *,
+                     logits_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """forward() for batches that still live in HOST memory (what the reference's callers hold
+        before `.to(device)`, src/train.py:252-255 / src/predict.py:220-238).
+
+        The batch is cut into micro-batches; a copy stream moves micro-batch i+1 host->device (pinned
+        memory makes the copies asynchronous) while the kernels of micro-batch i run, so the PCIe
+        transfer (602 KB per image) hides behind the compute.  Returns device tensors like forward().
+        """
+        eng = self._engine()
+        dev = eng.device
+        B = images.shape[0]
+        nc = self.num_classes
+        logits = logits_out if logits_out is not None else torch.empty(B, nc, dtype=torch.float32, device=dev)
+        probs = torch.empty(B, nc, dtype=torch.float32, device=dev)
+        if B == 0:
+            return {"logits": logits, "probs": probs}
+        mb = max(1, min(micro_batch, B))
+        main = torch.cuda.current_stream(dev)
+        copy = self.__dict__.get("_mrd_copy_stream")
+        if copy is None or copy.device != dev:
+            copy = torch.cuda.Stream(dev)
+            self.__dict__["_mrd_copy_stream"] = copy
+        staged = [None, None]       # device copies of the two micro-batches in flight
+        ready = [None, None]        # H2D finished
+        free = [None, None]         # kernels that read the staging slot finished
+        n_mb = -(-B // mb)
+
+        def issue_copy(i):
+            slot = i & 1
+            lo, hi = i * mb, min(B, (i + 1) * mb)
+            with torch.cuda.stream(copy):
+                if free[slot] is not None:
+                    copy.wait_event(free[slot])
+                m = None if attention_mask is None else attention_mask[lo:hi].to(dev, non_blocking=True)
+                staged[slot] = (images[lo:hi].to(dev, non_blocking=True),
+                                input_ids[lo:hi].to(dev, non_blocking=True), m)
+                ready[slot] = torch.cuda.Event()
+                ready[slot].record(copy)
+
+        copy.wait_stream(main)
+        issue_copy(0)
+        for i in range(n_mb):
+            if i + 1 < n_mb:
+                issue_copy(i + 1)
+            slot = i & 1
+            lo, hi = i * mb, min(B, (i + 1) * mb)
+            main.wait_event(ready[slot])
+            im, ids, m = staged[slot]
+            out = self.forward(im, ids, m, logits_out=logits[lo:hi])
+            probs[lo:hi].copy_(out["probs"])
+            for t in (im, ids, m):
+                if t is not None:
+                    t.record_stream(main)
+            free[slot] = torch.cuda.Event()
+            free[slot].record(main)
+        return {"logits": logits, "probs": probs}
+
 
 class ImageOnlyClassifier(B200Module):
     """src/multimodal_classifier.py:205-246."""

@@ -70,6 +70,24 @@ class DataParallelForward:
             parts.append(buf[r, : rhi - rlo])
         return torch.cat(parts, 0)
 
+    def forward_shard_host(self, host_forward: Callable, images, input_ids, attention_mask, total: int,
+                           device: torch.device) -> torch.Tensor:
+        """forward_shard for a shard that still lives in host memory: host_forward(images, ids, mask,
+        logits_out) streams it to the device in micro-batches (MultimodalClassifier.forward_host)."""
+        lo, hi = shard_bounds(total, self.world, self.rank)
+        n = hi - lo
+        if images.shape[0] != n:
+            raise ValueError(f"rank {self.rank} expects {n} samples, got {images.shape[0]}")
+        buf = self._buffer(total, device)
+        slot = buf[self.rank]
+        host_forward(images, input_ids, attention_mask, slot[:n])
+        if self.world > 1:
+            dist.all_gather_into_tensor(buf.view(-1), slot.reshape(-1), group=self.group)
+        if total == buf.shape[1] * self.world:
+            return buf.view(total, self.num_classes)
+        return torch.cat([buf[r, : shard_bounds(total, self.world, r)[1] - shard_bounds(total, self.world, r)[0]]
+                          for r in range(self.world)], 0)
+
     def forward_global(self, images, input_ids, attention_mask) -> torch.Tensor:
         """Inputs are the full batch (replicated on every rank); each rank computes its shard."""
         total = images.shape[0]

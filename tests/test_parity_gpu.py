@@ -239,3 +239,16 @@ def test_large_batch_properties(cuda, state):
     sd = state["sens"]
     ref = oracle.multimodal_forward(sd, images[:3], ids[:3], mask[:3])["logits"]
     _logits_ok(lg[:3], ref)
+
+
+def test_forward_host_streams_match_device_forward(cuda, state):
+    """forward_host (micro-batched H2D overlap) must return exactly what forward returns."""
+    model = _use(state, "sens")
+    images, ids, mask = synth.make_inputs(7, 32, 123, [32, 5, 17, 32, 1, 9, 20], H=64, W=64)
+    ref = _fwd(model, images, ids, mask)
+    with torch.no_grad():
+        out = model.forward_host(images.pin_memory(), ids.pin_memory(), mask.pin_memory(), micro_batch=3)
+        out2 = model.forward_host(images, ids, None, micro_batch=4)   # pageable memory, no mask
+    torch.cuda.synchronize()
+    assert torch.equal(out["logits"], ref["logits"]) and torch.equal(out["probs"], ref["probs"])
+    assert torch.equal(out2["logits"], _fwd(model, images, ids, None)["logits"])
