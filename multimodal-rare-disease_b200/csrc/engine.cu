@@ -121,7 +121,7 @@ struct mrd_ctx {
     std::unordered_map<const void*, size_t> weight_bytes;
 
     // options
-    int img_chunk = 128;
+    int img_chunk = 512;
     int tok_chunk = 131072;
     int bert_heads = 12;
     float bert_ln_eps = 1e-12f;
@@ -1180,6 +1180,7 @@ int mrd_ctx_profile(mrd_ctx* c, int enable) {
     }
     c->prof.clear();
     c->profiling = enable != 0;
+    gemm_set_pdl(!c->profiling);
     return 0;
 }
 

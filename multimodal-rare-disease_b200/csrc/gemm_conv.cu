@@ -29,6 +29,8 @@ namespace mrd {
 
 namespace {
 
+bool g_use_pdl = true;
+
 constexpr int kBlockM = 128;
 constexpr int kNumThreads = 352;  // TMA warp + MMA warp + 8 epilogue warps + residual-loader warp
 constexpr int kEpiThreads = 256;
@@ -126,6 +128,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) overlaps the tail of the previous kernel in the stream; nothing below may touch
+    // global memory before the previous grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     constexpr int NSUB = BLOCK_N / 64;
     const int num_k = p.num_taps * p.kc_per_tap;
@@ -359,8 +367,18 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
         attr_set = true;
     }
     const int smem = C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
-    kfn<<<g->grid, kNumThreads, smem, stream>>>(g->p);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g->grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, g->p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("conv_gemm_kernel<%d,%d> launch: %s", BLOCK_N, (int)STEM,
                        cudaGetErrorString(e));
@@ -422,6 +440,8 @@ int finish_plan(GemmLaunch* g, int block_n) {
 }
 
 }  // namespace
+
+void gemm_set_pdl(bool on) { g_use_pdl = on; }
 
 int gemm_num_sms() {
     static int sms = 0;

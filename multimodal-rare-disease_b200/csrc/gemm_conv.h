@@ -76,4 +76,8 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream);
 
 int gemm_num_sms();
 
+// Programmatic dependent launch for the GEMM/conv kernels (on by default; the engine turns it off
+// while profiling so that per-launch event timings do not overlap).
+void gemm_set_pdl(bool on);
+
 }  // namespace mrd

@@ -180,7 +180,7 @@ def test_invariances(cuda, state):
     try:
         d = _fwd(model, images, ids, mask)["logits"]
     finally:
-        model.configure_b200(img_chunk=128, seq_chunk_tokens=131072)
+        model.configure_b200(img_chunk=512, seq_chunk_tokens=131072)
     assert torch.equal(d, a), "results must not depend on the micro-batch tiling"
     pred, conf = model.predict(images.cuda(), ids.cuda(), mask.cuda())
     assert torch.equal(pred.cpu(), a.argmax(-1).cpu()) and conf.shape == (5,)
