@@ -59,39 +59,58 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// rows x 64 bf16 tile, global row stride ld (elements) -> swizzled smem (128 B per row)
+// rows x 64 bf16 tile, global row stride ld (elements) -> swizzled smem (128 B per row).  NT threads:
+// thread t always moves 16-byte chunk (t & 7) of rows (t >> 3) + k * NT/8, so the address arithmetic
+// is one pointer increment per row.
 template <int NT>
 __device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* base, long long ld,
                                           int row0, int rows, int S, int tid) {
-    for (int idx = tid; idx < rows * 8; idx += NT) {
-        const int r = idx >> 3, c = idx & 7;
-        const int grow = row0 + r;
-        const bool ok = grow < S;
-        const __nv_bfloat16* src = base + static_cast<long long>(ok ? grow : 0) * ld + c * 8;
-        cp_async16(dst + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+    const int c = tid & 7;
+    int r = tid >> 3;
+    const __nv_bfloat16* src = base + static_cast<long long>(row0 + r) * ld + c * 8;
+    uint32_t d = dst + r * 128 + ((c ^ (r & 7)) << 4);   // (r & 7) is invariant: rows advance by NT/8 = 16 or 32
+#pragma unroll
+    for (; r < rows; r += NT / 8) {
+        const bool ok = row0 + r < S;
+        cp_async16(d, ok ? src : base, ok);
+        src += static_cast<long long>(NT / 8) * ld;
+        d += (NT / 8) * 128;
     }
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // seq_off == null: dense layout, sample b owns rows [b*S_max, (b+1)*S_max) and mask_bias is [B,S_max].
 // seq_off != null: token-packed layout, sample b owns rows [seq_off[b], seq_off[b+1]) and mask_bias is
 // indexed by packed row.
+// One CTA = one (sample, BLOCK_M query rows, group of `hpg` heads).  The CTA walks its heads and their
+// 64-key blocks as one flat item list with a two-deep cp.async pipeline (the next item's K/V - and the
+// next head's Q - stream in while the current item is computed), so the global-load latency is paid
+// once per CTA instead of once per head.
 template <int BLOCK_M>
-__global__ void __launch_bounds__(BLOCK_M * 2, 2)
+__global__ void __launch_bounds__(BLOCK_M * 2, BLOCK_M == 64 ? 4 : 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask_bias,
-                 const int* __restrict__ seq_off, int S_max, int heads,
+                 const int* __restrict__ seq_off, int S_max, int heads, int hpg,
                  __nv_bfloat16* __restrict__ out) {
     constexpr int NT = BLOCK_M * 2;
+    constexpr int QBYTES = BLOCK_M * 128, KVBYTES = kBlockN * 128;
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t q_s = smem_u32(smem);
-    const uint32_t k_s = q_s + BLOCK_M * 128;
-    const uint32_t v_s = k_s + 2 * kBlockN * 128;
-    float* bias_s = reinterpret_cast<float*>(smem + BLOCK_M * 128 + 4 * kBlockN * 128);
+    const uint32_t q_s = smem_u32(smem);            // 2 Q buffers
+    const uint32_t k_s = q_s + 2 * QBYTES;          // 2 K buffers
+    const uint32_t v_s = k_s + 2 * KVBYTES;         // 2 V buffers
+    float* bias_s = reinterpret_cast<float*>(smem + 2 * QBYTES + 4 * KVBYTES);
     int* kb_list = reinterpret_cast<int*>(bias_s + kMaxS);
     int* nkb_s = kb_list + 8;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tq = lane & 3;
-    const int q0 = blockIdx.x * BLOCK_M, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * BLOCK_M, b = blockIdx.z;
+    const int h_begin = blockIdx.y * hpg;
+    const int nh = min(hpg, heads - h_begin);
     long long off;
     int S;
     if (seq_off) {
@@ -101,20 +120,32 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
         off = static_cast<long long>(b) * S_max;
         S = S_max;
     }
-    if (q0 >= S) return;  // uniform for the whole CTA
+    if (q0 >= S || nh <= 0) return;  // uniform for the whole CTA
     const long long ld = 3LL * heads * kHeadDim;
-    const __nv_bfloat16* q_base = qkv + off * ld + h * kHeadDim;
-    const __nv_bfloat16* k_base = q_base + heads * kHeadDim;
-    const __nv_bfloat16* v_base = k_base + heads * kHeadDim;
+    const long long ldo = static_cast<long long>(heads) * kHeadDim;
+    const __nv_bfloat16* row0 = qkv + off * ld;
 
-    // ---- key bias -> smem, list of key blocks that contain at least one attended key
+    // item = (head, key block); block 0 is always visited (it holds the CLS key), later blocks only
+    // when they contain an attended key
     const int nkb_total = (S + kBlockN - 1) / kBlockN;
+    auto issue = [&](int item, int nkb) {
+        const int hh = item / nkb, ki = item - hh * nkb;
+        const __nv_bfloat16* q_base = row0 + (h_begin + hh) * kHeadDim;
+        const int kb = ki == 0 ? 0 : kb_list[ki];
+        if (ki == 0) load_tile<NT>(q_s + (hh & 1) * QBYTES, q_base, ld, q0, BLOCK_M, S, tid);
+        load_tile<NT>(k_s + (item & 1) * KVBYTES, q_base + heads * kHeadDim, ld, kb * kBlockN, kBlockN, S, tid);
+        load_tile<NT>(v_s + (item & 1) * KVBYTES, q_base + 2 * heads * kHeadDim, ld, kb * kBlockN, kBlockN, S, tid);
+        cp_async_commit();
+    };
+    issue(0, 1 << 30);  // (head 0, block 0): does not depend on the bias pass below
+
     for (int i = tid; i < nkb_total * kBlockN; i += NT)
         bias_s[i] = i < S ? (mask_bias ? __ldg(mask_bias + off + i) : 0.0f) : -INFINITY;
     __syncthreads();
     if (warp == 0) {
-        int cnt = 0;
-        for (int kb = 0; kb < nkb_total; ++kb) {
+        int cnt = 1;
+        if (lane == 0) kb_list[0] = 0;
+        for (int kb = 1; kb < nkb_total; ++kb) {
             const bool v = bias_s[kb * kBlockN + lane] > -INFINITY ||
                            bias_s[kb * kBlockN + 32 + lane] > -INFINITY;
             if (__any_sync(0xffffffffu, v)) {
@@ -126,68 +157,89 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
     }
     __syncthreads();
     const int nkb = *nkb_s;
+    const int items = nh * nkb;
+
+    // a warp whose 16 query rows all lie beyond the sequence only helps with the loads
+    const bool warp_active = q0 + warp * 16 < S;
 
     float o[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     uint32_t qf[4][4];
 
-    if (nkb > 0) {
-        load_tile<NT>(q_s, q_base, ld, q0, BLOCK_M, S, tid);
-        load_tile<NT>(k_s, k_base, ld, kb_list[0] * kBlockN, kBlockN, S, tid);
-        load_tile<NT>(v_s, v_base, ld, kb_list[0] * kBlockN, kBlockN, S, tid);
-        cp_async_commit();
+    // per-lane ldmatrix offsets (swizzled), computed once: K tiles are read as [key][d] 8x8 blocks,
+    // V tiles transposed
+    const int mi = lane >> 3, x7 = lane & 7;
+    const uint32_t k_row = static_cast<uint32_t>(((mi >> 1) * 8 + x7) * 128);
+    const uint32_t v_row = static_cast<uint32_t>(((mi & 1) * 8 + x7) * 128);
+    uint32_t k_col[4], v_col[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k_col[i] = static_cast<uint32_t>(((i * 2 + (mi & 1)) ^ x7) << 4);
+        v_col[i] = static_cast<uint32_t>(((i * 2 + (mi >> 1)) ^ x7) << 4);
     }
 
-    for (int it = 0; it < nkb; ++it) {
-        const int buf = it & 1;
-        if (it + 1 < nkb) {
-            const int nb = kb_list[it + 1] * kBlockN;
-            load_tile<NT>(k_s + (buf ^ 1) * kBlockN * 128, k_base, ld, nb, kBlockN, S, tid);
-            load_tile<NT>(v_s + (buf ^ 1) * kBlockN * 128, v_base, ld, nb, kBlockN, S, tid);
-            cp_async_commit();
+    for (int item = 0; item < items; ++item) {
+        const int buf = item & 1;
+        if (item + 1 < items) {
+            issue(item + 1, nkb);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
 
-        if (it == 0) {
+        if (!warp_active) {
+            __syncthreads();
+            continue;
+        }
+        const int hh = item / nkb, ki = item - hh * nkb;
+        const int kb = kb_list[ki];
+        const uint32_t qbuf = q_s + (hh & 1) * QBYTES;
+        // keys of this block that exist: 8-key MMA tiles beyond them are skipped (their scores stay
+        // 0 + (-inf) bias, their probabilities 0)
+        const int nvalid = min(kBlockN, S - kb * kBlockN);
+        if (ki == 0) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int r = warp * 16 + (lane & 15);
                 const int c = kk * 2 + (lane >> 4);
-                ldmatrix_x4(q_s + r * 128 + ((c ^ (r & 7)) << 4), qf[kk][0], qf[kk][1], qf[kk][2],
+                ldmatrix_x4(qbuf + r * 128 + ((c ^ (r & 7)) << 4), qf[kk][0], qf[kk][1], qf[kk][2],
                             qf[kk][3]);
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+            m0 = m1 = -INFINITY;
+            l0 = l1 = 0.0f;
         }
 
         // ---- S = Q K^T (16 x 64 per warp)
         float s[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
-        const uint32_t kt = k_s + buf * kBlockN * 128;
+        const uint32_t kt = k_s + buf * KVBYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
-                const int mi = lane >> 3;
-                const int r = np * 16 + (mi >> 1) * 8 + (lane & 7);
-                const int c = kk * 2 + (mi & 1);
+                if (np * 16 >= nvalid) break;
                 uint32_t b0, b1, b2, b3;
-                ldmatrix_x4(kt + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+                ldmatrix_x4(kt + np * 2048 + k_row + k_col[kk], b0, b1, b2, b3);
                 mma_bf16(s[np * 2], qf[kk], b0, b1);
                 mma_bf16(s[np * 2 + 1], qf[kk], b2, b3);
             }
         }
 
         // ---- online softmax (rows g and g+8 of this warp's 16)
-        const float* bb = bias_s + kb_list[it] * kBlockN + tq * 2;
+        const float* bb = bias_s + kb * kBlockN + tq * 2;
         float mx0 = m0, mx1 = m1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float b0 = bb[j * 8], b1 = bb[j * 8 + 1];
+            if (j * 8 >= nvalid) {  // no key in this 8-wide tile: probabilities are exactly 0
+                s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY;
+                continue;
+            }
+            const float2 b01 = *reinterpret_cast<const float2*>(bb + j * 8);
+            const float b0 = b01.x, b1 = b01.y;
             s[j][0] += b0; s[j][1] += b1; s[j][2] += b0; s[j][3] += b1;
             mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
             mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
@@ -198,8 +250,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mu0 = mx0 == -INFINITY ? 0.0f : mx0;
         const float mu1 = mx1 == -INFINITY ? 0.0f : mx1;
-        const float corr0 = exp2f((m0 - mu0) * kLog2e);
-        const float corr1 = exp2f((m1 - mu1) * kLog2e);
+        const float corr0 = fast_exp2((m0 - mu0) * kLog2e);
+        const float corr1 = fast_exp2((m1 - mu1) * kLog2e);
         m0 = mx0; m1 = mx1;
         l0 *= corr0; l1 *= corr1;
 #pragma unroll
@@ -209,18 +261,23 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
         const float ms0 = mu0 * kLog2e, ms1 = mu1 * kLog2e;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = exp2f(fmaf(s[j][0], kLog2e, -ms0));
-            s[j][1] = exp2f(fmaf(s[j][1], kLog2e, -ms0));
-            s[j][2] = exp2f(fmaf(s[j][2], kLog2e, -ms1));
-            s[j][3] = exp2f(fmaf(s[j][3], kLog2e, -ms1));
+            if (j * 8 >= nvalid) {
+                s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+                continue;
+            }
+            s[j][0] = fast_exp2(fmaf(s[j][0], kLog2e, -ms0));
+            s[j][1] = fast_exp2(fmaf(s[j][1], kLog2e, -ms0));
+            s[j][2] = fast_exp2(fmaf(s[j][2], kLog2e, -ms1));
+            s[j][3] = fast_exp2(fmaf(s[j][3], kLog2e, -ms1));
             l0 += s[j][0] + s[j][1];
             l1 += s[j][2] + s[j][3];
         }
 
         // ---- O += P V
-        const uint32_t vt = v_s + buf * kBlockN * 128;
+        const uint32_t vt = v_s + buf * KVBYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
+            if (kk * 16 >= nvalid) break;
             uint32_t a[4];
             a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
             a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
@@ -228,54 +285,53 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
             a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
             for (int dp = 0; dp < 4; ++dp) {
-                const int mi = lane >> 3;
-                const int r = kk * 16 + (mi & 1) * 8 + (lane & 7);
-                const int c = dp * 2 + (mi >> 1);
                 uint32_t b0, b1, b2, b3;
-                ldmatrix_x4_trans(vt + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+                ldmatrix_x4_trans(vt + kk * 2048 + v_row + v_col[dp], b0, b1, b2, b3);
                 mma_bf16(o[dp * 2], a, b0, b1);
                 mma_bf16(o[dp * 2 + 1], a, b2, b3);
             }
         }
-        __syncthreads();
-    }
 
-    // ---- normalise, stage through this warp's own Q rows, 16-byte coalesced stores
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = l0 > 0.0f ? 1.0f / l0 : 0.0f;
-    const float inv1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
-    uint8_t* q_gen = smem;
-    {
-        const int r0 = warp * 16 + g, r1 = r0 + 8;
+        if (ki == nkb - 1) {
+            // ---- head finished: normalise, stage through this warp's own rows of the head's Q
+            // buffer (already consumed into registers), 16-byte coalesced stores
+            float t0 = l0, t1 = l1;
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 1);
+            t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            const float inv0 = t0 > 0.0f ? 1.0f / t0 : 0.0f;
+            const float inv1 = t1 > 0.0f ? 1.0f / t1 : 0.0f;
+            uint8_t* q_gen = smem + (hh & 1) * QBYTES;
+            const int r0 = warp * 16 + g, r1 = r0 + 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<uint32_t*>(q_gen + r0 * 128 + ((j ^ (r0 & 7)) << 4) + tq * 4) =
-                pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
-            *reinterpret_cast<uint32_t*>(q_gen + r1 * 128 + ((j ^ (r1 & 7)) << 4) + tq * 4) =
-                pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
-        }
-    }
-    __syncwarp();
-    const long long ldo = static_cast<long long>(heads) * kHeadDim;
+            for (int j = 0; j < 8; ++j) {
+                *reinterpret_cast<uint32_t*>(q_gen + r0 * 128 + ((j ^ (r0 & 7)) << 4) + tq * 4) =
+                    pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+                *reinterpret_cast<uint32_t*>(q_gen + r1 * 128 + ((j ^ (r1 & 7)) << 4) + tq * 4) =
+                    pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+            }
+            __syncwarp();
+            __nv_bfloat16* o_base = out + off * ldo + (h_begin + hh) * kHeadDim;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int idx = i * 32 + lane;
-        const int r = warp * 16 + (idx >> 3), c = idx & 7;
-        const int q = q0 + r;
-        if (q < S) {
-            const uint4 v = *reinterpret_cast<const uint4*>(q_gen + r * 128 + ((c ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(out + (off + q) * ldo + h * kHeadDim + c * 8) = v;
+            for (int i = 0; i < 4; ++i) {
+                const int idx = i * 32 + lane;
+                const int r = warp * 16 + (idx >> 3), c = idx & 7;
+                const int q = q0 + r;
+                if (q < S) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(q_gen + r * 128 + ((c ^ (r & 7)) << 4));
+                    *reinterpret_cast<uint4*>(o_base + q * ldo + c * 8) = v;
+                }
+            }
         }
+        __syncthreads();
     }
 }
 
 template <int BLOCK_M>
 int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
            int heads, __nv_bfloat16* out, cudaStream_t stream) {
-    constexpr int SMEM = BLOCK_M * 128 + 4 * kBlockN * 128 + kMaxS * 4 + 64;
+    constexpr int SMEM = 2 * BLOCK_M * 128 + 4 * kBlockN * 128 + kMaxS * 4 + 64;
     static bool attr_set = false;
     auto kfn = attention_kernel<BLOCK_M>;
     if (!attr_set) {
@@ -286,8 +342,13 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off,
         }
         attr_set = true;
     }
-    dim3 grid((S + BLOCK_M - 1) / BLOCK_M, heads, B);
-    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, seq_off, S, heads, out);
+    // heads per CTA: enough CTAs to fill the machine a few times over, as few pipeline ramps as possible
+    const long long base = static_cast<long long>((S + BLOCK_M - 1) / BLOCK_M) * B;
+    int hpg = heads;
+    while (hpg > 1 && base * ((heads + hpg - 1) / hpg) < 148LL * 8) hpg = (hpg + 1) / 2;
+    if (hpg > 4) hpg = 4;
+    dim3 grid((S + BLOCK_M - 1) / BLOCK_M, (heads + hpg - 1) / hpg, B);
+    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, seq_off, S, heads, hpg, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention_kernel<%d> launch: %s", BLOCK_M, cudaGetErrorString(e));
@@ -308,7 +369,7 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     }
     // 64-row query blocks when sequences are short (or packed to short lengths): a block whose rows
     // all lie beyond the sequence exits immediately; 128-row blocks halve the K/V re-reads otherwise
-    if (S > 128 || (S > 64 && seq_off == nullptr))
+    if (S > 64)
         return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
     return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
 }

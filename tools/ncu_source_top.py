@@ -34,3 +34,8 @@ print("by warp-instructions:", op_i.most_common(16), "total", sum(op_i.values())
 for r in sorted(data, key=lambda r: -int(r[si]))[:24]:
     st = {hdr[i][6:]: int(r[i]) for i in stall_cols if int(r[i]) > 0}
     print(r[si], r[ie], r[src].strip()[:64], dict(sorted(st.items(), key=lambda kv: -kv[1])[:3]))
+tot_st = collections.Counter()
+for r in data:
+    for i in stall_cols:
+        tot_st[hdr[i][6:]] += int(r[i])
+print("stall totals:", tot_st.most_common(12))
