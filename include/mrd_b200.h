@@ -126,10 +126,18 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
 
 /* Conv2d(k in {1,3}, stride in {1,2}, pad k/2, no bias) + folded BatchNorm + optional residual +
  * activation on NHWC bf16 (TV:143-163).  Wt: [Cout][k][k][Cin] bf16 with the BN scale folded in,
- * bias: f32 [Cout] = beta - mean*scale.  Cin % 64 == 0, Cout % 64 == 0. */
+ * bias: f32 [Cout] = beta - mean*scale.  Cin % 64 == 0, Cout % 64 == 0.
+ * out_pad = 1: Y is a zero-bordered [N][H/stride+2][W/stride+2][Cout] tensor and only its interior is
+ * written (the input layout of mrd_conv3x3_flat_bf16). */
 int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void* Wt, int Cout,
                          int ksize, int stride, const float* bias, void* Y, const void* residual,
-                         int act, void* stream);
+                         int act, int out_pad, void* stream);
+
+/* Conv2d(3, stride 1, pad 1) + folded BN + activation in flat-shift mode: Xpad is the zero-bordered
+ * [N][H+2][W+2][Cin] bf16 input; the halo span of each tile is fetched once per 64-channel chunk and
+ * the 9 taps are row-shifted tcgen05 views of it (TV:143-163 conv2 of layer1/layer2).  W <= 62. */
+int mrd_conv3x3_flat_bf16(const void* Xpad, int N, int H, int W, int Cin, const void* Wt, int Cout,
+                          const float* bias, void* Y, int act, void* stream);
 
 /* ResNet stem: Conv2d(3,64,7,stride 2,pad 3) + BN + ReLU (TV:197-199,268-270) on the repacked image
  * Xpad [N][H+6][W+8][4] bf16; Wst [64][7][32] bf16; Y [N,H/2,W/2,64] bf16. */

@@ -28,12 +28,22 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
 
 int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void* Wt, int Cout,
                          int ksize, int stride, const float* bias, void* Y, const void* residual,
-                         int act, void* stream) {
+                         int act, int out_pad, void* stream) {
     GemmLaunch g;
     int rc = plan_conv(&g, static_cast<const __nv_bfloat16*>(X), N, H, W, Cin,
                        static_cast<const __nv_bfloat16*>(Wt), Cout, ksize, stride, bias,
                        static_cast<__nv_bfloat16*>(Y), static_cast<const __nv_bfloat16*>(residual),
-                       act);
+                       act, out_pad);
+    if (rc) return rc;
+    return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_conv3x3_flat_bf16(const void* Xpad, int N, int H, int W, int Cin, const void* Wt, int Cout,
+                          const float* bias, void* Y, int act, void* stream) {
+    GemmLaunch g;
+    int rc = plan_conv3x3_flat(&g, static_cast<const __nv_bfloat16*>(Xpad), N, H, W, Cin,
+                               static_cast<const __nv_bfloat16*>(Wt), Cout, bias,
+                               static_cast<__nv_bfloat16*>(Y), act);
     if (rc) return rc;
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }

@@ -165,6 +165,11 @@ struct mrd_ctx {
     // cnn chunk buffers
     bf16 *xpad = nullptr, *stem_out = nullptr, *act0 = nullptr, *act1 = nullptr, *mid0 = nullptr,
          *mid1 = nullptr, *dsb = nullptr;
+    struct PadBuf {  // zero-bordered [Bc][h+2][w+2][c] input of a flat-mode 3x3 convolution
+        int h = 0, w = 0, c = 0;
+        bf16* p = nullptr;
+    };
+    std::vector<PadBuf> pads;
     // text chunk buffers
     bf16 *t_h = nullptr, *t_h2 = nullptr, *t_qkv = nullptr, *t_ctx = nullptr, *t_tmp = nullptr,
          *t_ffn = nullptr;
@@ -502,16 +507,43 @@ int load_head(mrd_ctx* c, const Table& t, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ workspaces and plans
+// 3x3 stride-1 convolutions on mid-sized feature maps run in flat-shift mode (plan_conv3x3_flat): the
+// tile is th = 128/(w+2) whole padded rows, so the M efficiency is th*w/128; below ~20 columns the
+// classic per-tap boxes (which can pack several rows/images per tile) win.
+inline bool flat3_eligible(const ConvW& cv, int h, int w) {
+    return cv.k == 3 && cv.stride == 1 && w >= 20 && conv3x3_flat_supported(h, w, cv.cin, cv.cout);
+}
+
 int ensure_cnn_ws(mrd_ctx* c, int H, int W) {
     const int Bc = c->img_chunk;
     if (c->cnn_ws.base && c->cnn_ws_B == Bc && c->cnn_ws_H == H && c->cnn_ws_W == W) return 0;
     c->cnn_plans.clear();
+    c->pads.clear();
+    {
+        int h = H / 4, w = W / 4;
+        for (const Bottleneck& b : c->blocks) {
+            if (flat3_eligible(b.c2, h, w)) {
+                bool have = false;
+                for (auto& pb : c->pads) have |= (pb.h == h && pb.w == w && pb.c == b.c2.cin);
+                if (!have) {
+                    mrd_ctx::PadBuf pb;
+                    pb.h = h; pb.w = w; pb.c = b.c2.cin;
+                    c->pads.push_back(pb);
+                }
+            }
+            h /= b.c2.stride;
+            w /= b.c2.stride;
+        }
+    }
     const long long q = 1LL * (H / 4) * (W / 4);  // pixels after stem + maxpool
     const long long n_xpad = 1LL * Bc * (H + 6) * (W + 8) * 4;
     const long long n_stem = 1LL * Bc * (H / 2) * (W / 2) * 64;
     const long long n_act = 1LL * Bc * q * 256;   // largest block output (layer1)
     const long long n_mid = 1LL * Bc * q * 128;   // largest bottleneck intermediate (layer2.0.conv1)
     size_t total = pad1k(n_xpad, 2) + pad1k(n_stem, 2) + 3 * pad1k(n_act, 2) + 2 * pad1k(n_mid, 2);
+    size_t pad_bytes = 0;
+    for (auto& pb : c->pads) pad_bytes += pad1k(1LL * Bc * (pb.h + 2) * (pb.w + 2) * pb.c, 2);
+    total += pad_bytes;
     MRD_TRY(arena_reset(c, &c->cnn_ws, total));
     c->xpad = arena_take<bf16>(&c->cnn_ws, n_xpad);
     c->stem_out = arena_take<bf16>(&c->cnn_ws, n_stem);
@@ -520,6 +552,16 @@ int ensure_cnn_ws(mrd_ctx* c, int H, int W) {
     c->dsb = arena_take<bf16>(&c->cnn_ws, n_act);
     c->mid0 = arena_take<bf16>(&c->cnn_ws, n_mid);
     c->mid1 = arena_take<bf16>(&c->cnn_ws, n_mid);
+    if (!c->pads.empty()) {
+        bf16* first = nullptr;
+        for (auto& pb : c->pads) {
+            pb.p = arena_take<bf16>(&c->cnn_ws, 1LL * Bc * (pb.h + 2) * (pb.w + 2) * pb.c);
+            if (!first) first = pb.p;
+        }
+        // borders must be (and stay) zero: the producing 1x1 convolution only writes the interior
+        cudaError_t e = cudaMemset(first, 0, pad_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(padded conv inputs)");
+    }
     c->cnn_ws_B = Bc;
     c->cnn_ws_H = H;
     c->cnn_ws_W = W;
@@ -550,10 +592,22 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
             return -1;
         }
         bf16* y = bufs[cur ^ 1];
-        MRD_TRY(plan_conv(&bp.c1, x, B, h, w, b.c1.cin, b.c1.w, b.c1.cout, b.c1.k, 1, b.c1.b,
-                          c->mid0, nullptr, ACT_RELU));
-        MRD_TRY(plan_conv(&bp.c2, c->mid0, B, h, w, b.c2.cin, b.c2.w, b.c2.cout, b.c2.k,
-                          b.c2.stride, b.c2.b, c->mid1, nullptr, ACT_RELU));
+        bf16* pad = nullptr;
+        if (flat3_eligible(b.c2, h, w))
+            for (auto& pb : c->pads)
+                if (pb.h == h && pb.w == w && pb.c == b.c2.cin) pad = pb.p;
+        if (pad) {
+            // conv1 writes the interior of the zero-bordered buffer; conv2 reads it in flat-shift mode
+            MRD_TRY(plan_conv(&bp.c1, x, B, h, w, b.c1.cin, b.c1.w, b.c1.cout, b.c1.k, 1, b.c1.b, pad,
+                              nullptr, ACT_RELU, 1));
+            MRD_TRY(plan_conv3x3_flat(&bp.c2, pad, B, h, w, b.c2.cin, b.c2.w, b.c2.cout, b.c2.b,
+                                      c->mid1, ACT_RELU));
+        } else {
+            MRD_TRY(plan_conv(&bp.c1, x, B, h, w, b.c1.cin, b.c1.w, b.c1.cout, b.c1.k, 1, b.c1.b,
+                              c->mid0, nullptr, ACT_RELU));
+            MRD_TRY(plan_conv(&bp.c2, c->mid0, B, h, w, b.c2.cin, b.c2.w, b.c2.cout, b.c2.k,
+                              b.c2.stride, b.c2.b, c->mid1, nullptr, ACT_RELU));
+        }
         const bf16* identity = x;
         bp.has_ds = b.has_ds;
         if (b.has_ds) {

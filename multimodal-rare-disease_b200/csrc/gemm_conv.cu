@@ -38,10 +38,13 @@ constexpr int kStageBufBytes = 128 * 128;  // one 128-row x 64-column bf16 sub-t
 constexpr int kSmemLimit = 232448;         // 227 KB opt-in limit per CTA
 constexpr int kMaxStages = 8;
 constexpr int kMaxRing = 8;
-constexpr int kBarBytes = 512;
+constexpr int kBarBytes = 1024;
 
-template <int BLOCK_N, bool STEM>
+constexpr int MODE_GENERIC = 0, MODE_STEM = 1, MODE_FLAT3 = 2;
+
+template <int BLOCK_N, int MODE>
 struct Cfg {
+    static constexpr bool STEM = MODE == MODE_STEM;
     static constexpr int BLOCK_K = STEM ? 32 : 64;
     static constexpr int ROW_BYTES = BLOCK_K * 2;
     static constexpr int A_STAGE = kBlockM * ROW_BYTES;
@@ -65,7 +68,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
     int r = m_idx / p.tiles_w;
     int th_i = r % p.tiles_h;
     int img_i = r / p.tiles_h;
-    t.w0 = tw_i * p.tw;
+    t.w0 = tw_i * p.tw + p.w_shift;
     t.h0 = th_i * p.th;
     t.n0 = img_i * p.nb;
     return t;
@@ -75,26 +78,38 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 // one binary serves the compute-bound GEMMs (deep operand pipeline, no residual ring) and the
 // memory-bound short-K convolutions with residual (shallow operand pipeline, deep residual ring)):
 //   [stages x A_STAGE][stages x B_STAGE][2 x 16 KB store staging][ring x 16 KB residual][barriers]
-template <int BLOCK_N, bool STEM>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using C = Cfg<BLOCK_N, STEM>;
-    const int STAGES = p.stages;
+    using C = Cfg<BLOCK_N, MODE>;
+    constexpr bool STEM = MODE == MODE_STEM;
+    constexpr bool FLAT = MODE == MODE_FLAT3;
+    constexpr bool WRES = STEM || FLAT;  // weights-resident modes
+    const int STAGES = p.stages;      // operand stages (WRES: A stages, one per tile / channel chunk)
     const int RING = p.ring;
+    // WRES: the whole weight panel of this CTA's output channels stays in shared memory for the
+    // lifetime of the (persistent) CTA and an A stage holds everything one tile needs - the 7 tap-row
+    // boxes of the stem, or one halo span of a flat 3x3 tile - so the MMA warp waits on ONE barrier
+    // per stage and then issues 14 / 36 back-to-back tcgen05.mma.  With N = 64 an MMA occupies the
+    // tensor core for only 32 cycles; a barrier round trip per 64-wide K block (the generic path)
+    // makes such layers issue-bound.
+    const int a_stage_bytes = WRES ? p.a_stage_bytes : C::A_STAGE;
+    const int b_region = WRES ? p.b_res_bytes : STAGES * C::B_STAGE;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
     const uint32_t a_smem = smem_base;
-    const uint32_t b_smem = a_smem + STAGES * C::A_STAGE;
-    const uint32_t st_smem = b_smem + STAGES * C::B_STAGE;
+    const uint32_t b_smem = a_smem + STAGES * a_stage_bytes;
+    const uint32_t st_smem = b_smem + b_region;
     const uint32_t ring_smem = st_smem + 2 * kStageBufBytes;
     const uint32_t bar_smem = ring_smem + RING * kStageBufBytes;
     uint8_t* st_gen = smem_gen + (st_smem - smem_base);
     uint8_t* ring_gen = smem_gen + (ring_smem - smem_base);
     volatile uint32_t* tmem_slot =
         reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_smem - smem_base) + 320);
+    const uint32_t bres_bar = bar_smem + 384u;  // WRES: resident weights have landed
 
     auto full_bar = [&](int s) { return bar_smem + 8u * s; };
     auto empty_bar = [&](int s) { return bar_smem + 64u + 8u * s; };
@@ -121,6 +136,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
         }
+        mbar_init(bres_bar, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 320);
@@ -149,7 +165,129 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     const int my_tiles = total_tiles > bid ? (total_tiles - bid + nblk - 1) / nblk : 0;
 
-    if (warp == 0) {
+    if (warp == 0 && WRES) {
+        // ------------------------------------------------------------ TMA producer, weights-resident modes
+        // FLAT: the activation is a zero-bordered [N][H+2][W+2][Cin] tensor seen as a flat list of
+        // pixel rows.  One 2-D box per 64-channel chunk brings in the whole halo span of the tile; the
+        // 9 taps are then row-shifted views of that span (UMMA descriptors may start at any 128-byte
+        // row of a swizzled region), so every input byte crosses L2->SMEM once instead of 9 times.
+        // STEM: the 7 tap-row boxes of a tile land in one stage under one barrier.
+        const int n_fixed = bid % p.n_tiles_n;  // grid is a multiple of n_tiles_n: constant per CTA
+        if (lane == 0) {
+            mbar_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes));
+            if constexpr (FLAT) {
+                for (int kc = 0; kc < p.kc_per_tap; ++kc)
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d(&p.b_map, bres_bar, b_smem + (kc * 9 + tap) * C::B_STAGE,
+                                    (tap * p.kc_per_tap + kc) * 64, n_fixed * BLOCK_N);
+            } else {
+                for (int tap = 0; tap < 7; ++tap)
+                    tma_load_2d(&p.b_map, bres_bar, b_smem + tap * C::B_STAGE, tap * C::BLOCK_K, 0);
+            }
+        }
+        __syncwarp();
+        int sa = 0;
+        uint32_t pa = 0;
+        const uint32_t span_bytes = static_cast<uint32_t>(p.span_rows) * 128u;
+        // With whole-tile stages only 2-3 loads are in flight per SM, too few to cover HBM latency:
+        // the tiles kPrefetch iterations ahead are pulled into L2 with bulk prefetches (no smem).
+        constexpr int kPrefetch = 0;  // measured: no gain for the flat mode, a loss for the stem (r01)
+        auto prefetch_tile = [&](int tile) {
+            if (tile >= total_tiles || lane != 0) return;
+            const TileCoord t = decode_tile(p, tile);
+            if constexpr (FLAT) {
+                const int f_start = (t.n0 * (p.Ho + 2) + t.h0) * p.tw;
+                for (int kc = 0; kc < p.kc_per_tap; ++kc) tma_prefetch_2d(&p.a_map[0], kc * 64, f_start);
+            } else {
+                for (int tap = 0; tap < 7; ++tap) tma_prefetch_5d(&p.a_map[0], 0, t.w0, t.h0, tap, t.n0);
+            }
+        };
+        if (kPrefetch > 0)
+            for (int i = 1; i < kPrefetch; ++i) prefetch_tile(bid + i * nblk);
+        for (int tile = bid; tile < total_tiles; tile += nblk) {
+            const TileCoord t = decode_tile(p, tile);
+            if (kPrefetch > 0) prefetch_tile(tile + kPrefetch * nblk);
+            if constexpr (FLAT) {
+                // tile row i = padded pixel (h0+1, 1) + i in flat order; its halo span starts one padded
+                // row and one pixel earlier, i.e. at padded pixel (h0, 0)  (tw == W+2)
+                const int f_start = (t.n0 * (p.Ho + 2) + t.h0) * p.tw;
+                for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                    mbar_wait(empty_bar(sa), pa ^ 1u);
+                    if (lane == 0) {
+                        mbar_expect_tx(full_bar(sa), span_bytes);
+                        tma_load_2d(&p.a_map[0], full_bar(sa), a_smem + sa * a_stage_bytes, kc * 64, f_start);
+                    }
+                    __syncwarp();
+                    if (++sa == STAGES) { sa = 0; pa ^= 1u; }
+                }
+            } else {
+                mbar_wait(empty_bar(sa), pa ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(full_bar(sa), 7u * a_box_bytes);
+                    for (int tap = 0; tap < 7; ++tap)
+                        tma_load_5d(&p.a_map[0], full_bar(sa), a_smem + sa * a_stage_bytes + tap * C::A_STAGE,
+                                    0, t.w0, t.h0, tap, t.n0);
+                }
+                __syncwarp();
+                if (++sa == STAGES) { sa = 0; pa ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && WRES) {
+        // ------------------------------------------------------------ MMA issuer, weights-resident modes
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        int sa = 0;
+        uint32_t pa = 0;
+        int it = 0;
+        mbar_wait(bres_bar, 0);
+        for (int tile = bid; tile < total_tiles; tile += nblk, ++it) {
+            const int acc = it & 1;
+            mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            if constexpr (FLAT) {
+                for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                    mbar_wait(full_bar(sa), pa);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = a_smem + sa * a_stage_bytes;
+                        const uint32_t b0 = b_smem + kc * 9 * C::B_STAGE;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int tap_row = (tap / 3) * p.tw + (tap % 3);  // row shift of this tap's view
+                            const uint64_t adesc = make_smem_desc(a0 + tap_row * 128, 0, C::SBO, C::LAYOUT);
+                            const uint64_t bdesc = make_smem_desc(b0 + tap * C::B_STAGE, 0, C::SBO, C::LAYOUT);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                          (kc | tap | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(empty_bar(sa));
+                        if (kc == p.kc_per_tap - 1) umma_commit(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++sa == STAGES) { sa = 0; pa ^= 1u; }
+                }
+            } else {
+                mbar_wait(full_bar(sa), pa);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int tap = 0; tap < 7; ++tap) {
+                        const uint64_t adesc = make_smem_desc(a_smem + sa * a_stage_bytes + tap * C::A_STAGE,
+                                                              0, C::SBO, C::LAYOUT);
+                        const uint64_t bdesc = make_smem_desc(b_smem + tap * C::B_STAGE, 0, C::SBO, C::LAYOUT);
+#pragma unroll
+                        for (int k = 0; k < C::BLOCK_K / 16; ++k)
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(sa));
+                    umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++sa == STAGES) { sa = 0; pa ^= 1u; }
+            }
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
@@ -161,15 +299,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t a_dst = a_smem + stage * C::A_STAGE;
                     const uint32_t b_dst = b_smem + stage * C::B_STAGE;
-                    if constexpr (STEM) {
-                        tma_load_5d(&p.a_map[0], full_bar(stage), a_dst, 0, t.w0, t.h0, ks, t.n0);
-                    } else {
-                        const int tap = ks / p.kc_per_tap;
-                        const int kc = ks - tap * p.kc_per_tap;
-                        const TapDesc td = p.taps[tap];
-                        tma_load_4d(&p.a_map[td.map], full_bar(stage), a_dst, kc * C::BLOCK_K,
-                                    t.w0 + td.dw, t.h0 + td.dh, t.n0);
-                    }
+                    const int tap = ks / p.kc_per_tap;
+                    const int kc = ks - tap * p.kc_per_tap;
+                    const TapDesc td = p.taps[tap];
+                    tma_load_4d(&p.a_map[td.map], full_bar(stage), a_dst, kc * C::BLOCK_K,
+                                t.w0 + td.dw, t.h0 + td.dh, t.n0);
                     tma_load_2d(&p.b_map, full_bar(stage), b_dst, ks * C::BLOCK_K,
                                 t.n_idx * BLOCK_N);
                 }
@@ -352,11 +486,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
 }
 
-template <int BLOCK_N, bool STEM>
+template <int BLOCK_N, int MODE>
 int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
-    using C = Cfg<BLOCK_N, STEM>;
+    using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
-    auto kfn = conv_gemm_kernel<BLOCK_N, STEM>;
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE>;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -366,7 +500,9 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    const int smem = C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
+    const int smem = MODE != MODE_GENERIC
+                         ? C::FIXED + g->p.stages * g->p.a_stage_bytes + g->p.b_res_bytes
+                         : C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g->grid);
     cfg.blockDim = dim3(kNumThreads);
@@ -380,7 +516,7 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
     cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, g->p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_last_error("conv_gemm_kernel<%d,%d> launch: %s", BLOCK_N, (int)STEM,
+        set_last_error("conv_gemm_kernel<%d,%d> launch: %s", BLOCK_N, MODE,
                        cudaGetErrorString(e));
         return -static_cast<int>(e);
     }
@@ -433,9 +569,15 @@ int finish_plan(GemmLaunch* g, int block_n) {
         return -1;
     }
     p.total_tiles = static_cast<int>(total);
-    pick_pipeline(&p, block_n, g->stem != 0);
     const int sms = gemm_num_sms();
     g->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (g->flat3 || g->stem) {
+        // weights-resident: every CTA keeps one n-tile's weights, so its tiles must share n_idx
+        g->grid = g->grid / p.n_tiles_n * p.n_tiles_n;
+        if (g->grid < p.n_tiles_n) g->grid = p.n_tiles_n;
+    } else {
+        pick_pipeline(&p, block_n, false);
+    }
     return 0;
 }
 
@@ -527,8 +669,8 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
 
 int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Cin,
               const __nv_bfloat16* Wt, int Cout, int ksize, int stride, const float* bias,
-              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act) {
-    if (ksize == 1 && stride == 1) {
+              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act, int out_pad) {
+    if (ksize == 1 && stride == 1 && out_pad == 0) {
         const long long M = static_cast<long long>(N) * H * W;
         if (M > 0x7fffffffLL) {
             set_last_error("plan_conv: M too large");
@@ -621,18 +763,115 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
         if (rc) return rc;
     }
     {
+        // out_pad: Y is a zero-bordered [N][Ho+2p][Wo+2p][Cout] tensor; only its interior is written
+        const int Wy = Wo + 2 * out_pad, Hy = Ho + 2 * out_pad;
+        __nv_bfloat16* y0 = Y + (static_cast<long long>(out_pad) * Wy + out_pad) * Cout;
         uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2,
-                           (uint64_t)Ho * Wo * Cout * 2};
+        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wy * Cout * 2,
+                           (uint64_t)Hy * Wy * Cout * 2};
         uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
-        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        int rc = encode_tensor_map(&p.c_map, y0, 2, 4, dims, str, box, 128);
         if (rc) return rc;
         p.r_map = p.c_map;
         if (residual) {
+            if (out_pad) {
+                set_last_error("plan_conv: residual with a padded output is not supported");
+                return -1;
+            }
             rc = encode_tensor_map(&p.r_map, residual, 2, 4, dims, str, box, 128);
             if (rc) return rc;
         }
     }
+    return finish_plan(g, bn);
+}
+
+bool conv3x3_flat_supported(int H, int W, int Cin, int Cout) {
+    const int Wp = W + 2;
+    if (H < 1 || W < 1 || Wp > 128 || Cin % 64 != 0 || Cout % 64 != 0) return false;
+    const int th = 128 / Wp;
+    if ((th + 2) * Wp + 2 > 256) return false;
+    int rows_alloc = 2 * Wp + 2 + 128;
+    if (rows_alloc < (th + 2) * Wp + 2) rows_alloc = (th + 2) * Wp + 2;
+    const int a_stage = ((rows_alloc * 128) + 1023) / 1024 * 1024;
+    const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
+    return fixed + 2 * a_stage + 9 * (Cin / 64) * 64 * 128 <= kSmemLimit;
+}
+
+int plan_conv3x3_flat(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W, int Cin,
+                      const __nv_bfloat16* Wt, int Cout, const float* bias, __nv_bfloat16* Y, int act) {
+    memset(g, 0, sizeof(*g));
+    const int Wp = W + 2, Hp = H + 2;
+    const int th = 128 / Wp;
+    if (th < 1 || Cin % 64 != 0 || Cout % 64 != 0 || N <= 0) {
+        set_last_error("plan_conv3x3_flat: unsupported shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
+        return -1;
+    }
+    ConvGemmParams& p = g->p;
+    g->flat3 = 1;
+    int rows_alloc = 2 * Wp + 2 + 128;  // the MMA reads 128 rows from any tap offset (<= 2*Wp + 2)
+    if (rows_alloc < (th + 2) * Wp + 2) rows_alloc = (th + 2) * Wp + 2;
+    const int a_stage = ((rows_alloc * 128) + 1023) / 1024 * 1024;
+    const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
+    // widest N tile whose whole 3x3 weight panel fits next to two halo-span stages
+    int bn = 0;
+    for (int cand : {128, 64})
+        if (Cout % cand == 0 && bn == 0 &&
+            fixed + 2 * a_stage + 9 * (Cin / 64) * cand * 128 <= kSmemLimit)
+            bn = cand;
+    if (bn == 0) {
+        set_last_error("plan_conv3x3_flat: weight panel of Cin=%d does not fit in shared memory", Cin);
+        return -1;
+    }
+    p.bias = bias;
+    p.has_res = 0;
+    p.num_taps = 9;
+    p.kc_per_tap = Cin / 64;
+    p.tw = Wp; p.th = th; p.nb = 1;
+    // tile row i is output pixel (h0 + i / (W+2), i % (W+2)): columns W and W+1 of every row are the
+    // right/left border positions of the flat order; the TMA store clips them (w >= W is out of bounds)
+    p.w_shift = 0;
+    p.tiles_w = 1; p.tiles_h = (H + th - 1) / th; p.tiles_img = N;
+    p.Wo = W; p.Ho = H; p.Nimg = N; p.Cout = Cout;
+    p.act = act;
+    p.store_bf16 = 1;
+    p.span_rows = (th + 2) * Wp + 2;
+    p.a_stage_bytes = a_stage;
+    if (p.span_rows > 256) {
+        set_last_error("plan_conv3x3_flat: halo span of %d rows exceeds the TMA box limit", p.span_rows);
+        return -1;
+    }
+    g->flops = 2.0 * N * H * W * static_cast<double>(Cout) * Cin * 9;
+    g->bytes = 2.0 * (1.0 * N * Hp * Wp * Cin + 9.0 * Cout * Cin + 1.0 * N * H * W * Cout);
+    {
+        const uint64_t R = static_cast<uint64_t>(N) * Hp * Wp;
+        uint64_t dims[2] = {(uint64_t)Cin, R};
+        uint64_t str[1] = {(uint64_t)Cin * 2};
+        uint32_t box[2] = {64, (uint32_t)p.span_rows};
+        int rc = encode_tensor_map(&p.a_map[0], Xpad, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+        for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    }
+    {
+        const uint64_t Kt = static_cast<uint64_t>(Cin) * 9;
+        uint64_t dims[2] = {Kt, (uint64_t)Cout};
+        uint64_t str[1] = {Kt * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = encode_tensor_map(&p.b_map, Wt, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, (uint32_t)Wp, (uint32_t)th, 1};
+        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+        p.r_map = p.c_map;
+    }
+    // pipeline: resident weight panel + as many halo-span stages as fit
+    p.b_res_bytes = 9 * (Cin / 64) * bn * 128;
+    p.ring = 0;
+    int st = (kSmemLimit - fixed - p.b_res_bytes) / a_stage;
+    p.stages = st > kMaxStages ? kMaxStages : st;
     return finish_plan(g, bn);
 }
 
@@ -689,15 +928,32 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
         if (rc) return rc;
         p.r_map = p.c_map;
     }
+    // weights-resident: 7 tap-row boxes (8 KB slots) per A stage, the 7 x 4 KB weight tiles resident
+    p.a_stage_bytes = 7 * 128 * 64;
+    p.b_res_bytes = 7 * 64 * 64;
+    p.ring = 0;
+    {
+        const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
+        int st = (kSmemLimit - fixed - p.b_res_bytes) / p.a_stage_bytes;
+        p.stages = st > kMaxStages ? kMaxStages : st;
+    }
     return finish_plan(g, 64);
 }
 
 int launch_gemm(const GemmLaunch* g, cudaStream_t stream) {
-    if (g->stem) return launch_variant<64, true>(g, stream);
+    if (g->stem) return launch_variant<64, MODE_STEM>(g, stream);
+    if (g->flat3) {
+        switch (g->block_n) {
+            case 64: return launch_variant<64, MODE_FLAT3>(g, stream);
+            case 128: return launch_variant<128, MODE_FLAT3>(g, stream);
+        }
+        set_last_error("launch_gemm: bad flat3 block_n %d", g->block_n);
+        return -1;
+    }
     switch (g->block_n) {
-        case 64: return launch_variant<64, false>(g, stream);
-        case 128: return launch_variant<128, false>(g, stream);
-        case 256: return launch_variant<256, false>(g, stream);
+        case 64: return launch_variant<64, MODE_GENERIC>(g, stream);
+        case 128: return launch_variant<128, MODE_GENERIC>(g, stream);
+        case 256: return launch_variant<256, MODE_GENERIC>(g, stream);
     }
     set_last_error("launch_gemm: bad block_n %d", g->block_n);
     return -1;

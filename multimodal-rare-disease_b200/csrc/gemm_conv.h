@@ -33,6 +33,8 @@ struct alignas(64) ConvGemmParams {
     const int* dyn_rows;            // optional (device): live GEMM rows <= M; tiles beyond are skipped
     int has_res;                    // 1: add the residual tile fetched through r_map
     int stages, ring;               // operand pipeline depth, residual ring depth (16 KB sub-tiles)
+    int w_shift;                    // added to the tile's first column (flat 3x3 mode: -1)
+    int span_rows, a_stage_bytes, b_res_bytes;  // weights-resident modes: halo span rows, A stage / weight panel bytes
     int num_taps;                   // 1, 7 (stem) or 9
     int kc_per_tap;                 // K chunks (of BLOCK_K) per tap
     TapDesc taps[9];
@@ -49,6 +51,7 @@ struct GemmLaunch {
     ConvGemmParams p;
     int block_n;  // 64, 128 or 256
     int stem;     // 1: 5-D overlapping-window A map, BLOCK_K = 32
+    int flat3;    // 1: flat-shift 3x3 stride-1 mode (halo span in smem, taps = row-shifted views)
     int grid;
     double flops;  // algorithmic FLOPs (2*M*N*K, un-padded), for reporting
     double bytes;  // algorithmic bytes: A + W read once, C written once (+ residual read)
@@ -63,9 +66,19 @@ int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int
 
 // ksize in {1,3}, stride in {1,2}, padding = ksize/2.  X: [N,H,W,Cin] bf16, Wt: [Cout][k][k][Cin]
 // bf16 (BN already folded), Y: [N,H/stride,W/stride,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0.
+// out_pad = 1: Y is a zero-bordered [N][Ho+2][Wo+2][Cout] tensor whose interior is written (feeds
+// plan_conv3x3_flat).
 int plan_conv(GemmLaunch* out, const __nv_bfloat16* X, int N, int H, int W, int Cin,
               const __nv_bfloat16* Wt, int Cout, int ksize, int stride, const float* bias,
-              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act);
+              __nv_bfloat16* Y, const __nv_bfloat16* residual, int act, int out_pad = 0);
+
+// 3x3 stride-1 pad-1 convolution in flat-shift mode.  Xpad: zero-bordered [N][H+2][W+2][Cin] bf16;
+// Wt: [Cout][3][3][Cin]; Y: [N,H,W,Cout] (unpadded).  The halo span of a tile is loaded once per
+// 64-channel chunk and the 9 taps are row-shifted UMMA views of it.  W <= 62.
+// (Cin/64) * 9 weight tiles must fit in shared memory next to two halo spans: see conv3x3_flat_supported.
+bool conv3x3_flat_supported(int H, int W, int Cin, int Cout);
+int plan_conv3x3_flat(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W, int Cin,
+                      const __nv_bfloat16* Wt, int Cout, const float* bias, __nv_bfloat16* Y, int act);
 
 // 7x7 stride-2 pad-3 stem.  Xpad: [N][H+6][W+8][4] bf16 (zero border, channel 3 zero),
 // Wst: [64][7][32] bf16 (tap row r, then 8 pixels x 4 channels; BN folded), Y: [N,H/2,W/2,64].

@@ -106,6 +106,20 @@ __device__ __forceinline__ void tma_load_5d(const void* map, uint32_t bar, uint3
         : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier): used by producers that
+// hold only a few large stages to pull the tiles they will need next from HBM into L2.
+__device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::
+                     "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const void* map, int c0, int c1, int c2, int c3,
+                                                int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::
+                     "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1,
                                              int c2, int c3) {
     asm volatile(

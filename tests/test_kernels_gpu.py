@@ -103,7 +103,7 @@ def _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res, seed=0):
     y = torch.full((N, Ho, Wo, Cout), float("nan"), device=cuda, dtype=BF)
     _check(lib, lib.mrd_conv2d_nhwc_bf16(x_nhwc.data_ptr(), N, H, W, Cin, w_ohwi.data_ptr(), Cout, k,
                                          stride, bias.data_ptr(), y.data_ptr(),
-                                         r_nhwc.data_ptr() if res else None, act, _stream()))
+                                         r_nhwc.data_ptr() if res else None, act, 0, _stream()))
     torch.cuda.synchronize()
     ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=k // 2)
     if res:
@@ -128,6 +128,50 @@ def _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res, seed=0):
 ])
 def test_conv(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res):
     _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,act", [
+    (3, 56, 56, 64, 64, 1),      # layer1 conv2: 2 padded rows per tile
+    (2, 28, 28, 128, 128, 1),    # layer2 conv2: 4 rows per tile, two 64-channel chunks
+    (5, 20, 24, 64, 128, 0),     # ragged: H not a multiple of th, non-square
+    (1, 28, 28, 128, 64, 1),
+    (70, 28, 28, 64, 64, 1),     # many tiles per CTA (persistence, ring wrap-around)
+])
+def test_conv3x3_flat(lib, cuda, N, H, W, Cin, Cout, act):
+    """1x1 conv writing the interior of a zero-bordered buffer, then the flat-shift 3x3 conv on it."""
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cin)
+    x = torch.randn(N, Cin, H, W, device=cuda, generator=g).to(BF)
+    w1 = (torch.randn(Cin, Cin, 1, 1, device=cuda, generator=g) / math.sqrt(Cin)).to(BF)
+    b1 = torch.randn(Cin, device=cuda, generator=g)
+    w3 = (torch.randn(Cout, Cin, 3, 3, device=cuda, generator=g) / math.sqrt(Cin * 9)).to(BF)
+    b3 = torch.randn(Cout, device=cuda, generator=g)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    pad = torch.zeros(N, H + 2, W + 2, Cin, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_conv2d_nhwc_bf16(x_nhwc.data_ptr(), N, H, W, Cin,
+                                         w1.permute(0, 2, 3, 1).contiguous().data_ptr(), Cin, 1, 1,
+                                         b1.data_ptr(), pad.data_ptr(), None, 1, 1, _stream()))
+    torch.cuda.synchronize()
+    mid = F.relu(F.conv2d(x.float(), w1.float(), b1))
+    _close(pad[:, 1:-1, 1:-1].permute(0, 3, 1, 2), mid, what="1x1 conv into padded buffer")
+    assert (pad[:, 0] == 0).all() and (pad[:, -1] == 0).all() and (pad[:, :, 0] == 0).all() \
+        and (pad[:, :, -1] == 0).all(), "borders of the padded buffer must stay zero"
+    y = torch.full((N, H, W, Cout), float("nan"), device=cuda, dtype=BF)
+    _check(lib, lib.mrd_conv3x3_flat_bf16(pad.data_ptr(), N, H, W, Cin,
+                                          w3.permute(0, 2, 3, 1).contiguous().data_ptr(), Cout,
+                                          b3.data_ptr(), y.data_ptr(), act, _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(pad[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float(), w3.float(), b3, padding=1)
+    if act == 1:
+        ref = F.relu(ref)
+    _close(y.permute(0, 3, 1, 2), ref, what=f"flat 3x3 conv {Cin}->{Cout} {H}x{W}")
+
+
+def test_conv3x3_flat_rejects_unsupported(lib, cuda):
+    # the resident 3x3 weight panel of Cin=128 does not fit next to two 56-wide halo spans
+    x = torch.zeros(1, 58, 58, 128, device=cuda, dtype=BF)
+    rc = lib.mrd_conv3x3_flat_bf16(x.data_ptr(), 1, 56, 56, 128, x.data_ptr(), 64, None, x.data_ptr(), 0,
+                                   _stream())
+    assert rc != 0 and b"shared memory" in lib.mrd_last_error()
 
 
 @pytest.mark.parametrize("N,H,W", [(2, 224, 224), (1, 64, 96), (3, 32, 32)])

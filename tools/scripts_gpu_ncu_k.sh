@@ -1,5 +1,5 @@
 #!/bin/bash
-# full ncu capture of one kernel family: KREGEX=... SKIP=n COUNT=n
+# full ncu capture of selected launches: KREGEX=... SKIP=n COUNT=n TAG=name GB=batch
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --global-batch ${GB:-256} --no-cpu-baseline --no-e2e"
