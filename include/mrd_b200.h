@@ -184,9 +184,13 @@ int mrd_compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_
                        int* row_tok, float* row_bias, int* n_rows, int* scratch, void* stream);
 
 /* mrd_attention_bf16 on the token-packed layout: sample b owns rows [seq_off[b], seq_off[b+1]) of qkv,
- * row_bias and out; max_len bounds the sequence lengths. */
+ * row_bias and out; max_len bounds the sequence lengths; total_rows = rows of qkv / out. */
 int mrd_attention_varlen_bf16(const void* qkv, const float* row_bias, const int* seq_off, int B,
-                              int max_len, int heads, void* out, void* stream);
+                              int max_len, int heads, long long total_rows, void* out, void* stream);
+
+/* Attention with max length <= 128 runs on tcgen05 (TMEM scores, TMA tiles); 0 forces the mma.sync
+ * kernel that serves longer sequences (process-wide test switch). */
+int mrd_attention_use_tcgen05(int on);
 
 /* attention_mask [B,S] -> additive key bias (0 / -inf). */
 int mrd_mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias, void* stream);

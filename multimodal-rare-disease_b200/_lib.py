@@ -57,7 +57,8 @@ SIGNATURES = {
     "mrd_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "mrd_mask_to_bias": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mrd_compact_tokens": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mrd_attention_varlen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mrd_attention_varlen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _vp, _vp]),
+    "mrd_attention_use_tcgen05": (_i, [_i]),
 }
 
 

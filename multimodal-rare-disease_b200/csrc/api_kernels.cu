@@ -106,14 +106,23 @@ int mrd_attention_bf16(const void* qkv, const float* mask_bias, int B, int S, in
 }
 
 int mrd_attention_varlen_bf16(const void* qkv, const float* row_bias, const int* seq_off, int B,
-                              int max_len, int heads, void* out, void* stream) {
+                              int max_len, int heads, long long total_rows, void* out, void* stream) {
     if (!seq_off) {
         set_last_error("mrd_attention_varlen_bf16: seq_off is required");
         return -1;
     }
+    if (total_rows <= 0) {
+        set_last_error("mrd_attention_varlen_bf16: total_rows must be the row count of qkv / out");
+        return -1;
+    }
     return attention_forward(static_cast<const __nv_bfloat16*>(qkv), row_bias, seq_off, B, max_len,
                              heads, static_cast<__nv_bfloat16*>(out),
-                             static_cast<cudaStream_t>(stream));
+                             static_cast<cudaStream_t>(stream), total_rows);
+}
+
+int mrd_attention_use_tcgen05(int on) {
+    attention_set_tc(on != 0);
+    return 0;
 }
 
 int mrd_compact_tokens(const void* mask, int mask_dtype, int B, int S, int keep_all, int* seq_off,

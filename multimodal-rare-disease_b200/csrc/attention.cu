@@ -21,6 +21,8 @@ namespace mrd {
 
 namespace {
 
+bool g_attention_tc = true;
+
 constexpr int kHeadDim = 64;
 constexpr int kBlockN = 64;
 constexpr int kMaxS = 512;
@@ -357,10 +359,228 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off,
     return 0;
 }
 
+// ====================================================================== tcgen05 path (S <= 128)
+// One work item = one (sample, head); all queries and keys of the sample fit one 128x128 tile.
+//   control warp (lane 0): TMA loads Q | K | V tiles (128 rows x 64 dims each, 128B-swizzled) straight
+//       from the [rows, 3*heads*64] qkv matrix, issues S = Q K^T (tcgen05.mma, N = keys rounded up to 16)
+//       into TMEM and later O = P V (V is the MN-major B operand exactly as TMA wrote it);
+//   4 softmax warps (thread = query row = TMEM lane): read their score row with tcgen05.ld, apply the
+//       key bias / length mask, exponentiate, write the bf16 probabilities as the K-major A operand of
+//       the second product over the (already consumed) Q/K tiles, then read O back, scale by 1/sum and
+//       store the row.
+// A CTA is strictly sequential per item; four CTAs share an SM (48 KB smem, 128 TMEM columns each), so
+// one CTA's softmax overlaps the other CTAs' loads and MMAs.
+constexpr int kTcThreads = 160;
+
+struct TcParams {
+    CUtensorMap qkv_map;
+    const float* bias;     // per row (packed) or [B,S] (dense); may be null
+    const int* seq_off;    // packed layout or null
+    __nv_bfloat16* out;
+    int S_max, heads, items;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 4)
+attention_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t q_s = base, k_s = base + 16384, v_s = base + 32768;  // P overlays Q and K
+    float* bias_s = reinterpret_cast<float*>(gen + 49152);
+    const uint32_t bars = base + 49152 + 512;
+    const uint32_t full_bar = bars, s_bar = bars + 8, p_bar = bars + 16, o_bar = bars + 24, t_bar = bars + 32;
+    volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 49152 + 512 + 64);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tma_prefetch_desc(&p.qkv_map);
+        mbar_init(full_bar, 1);
+        mbar_init(s_bar, 1);
+        mbar_init(p_bar, 128);
+        mbar_init(o_bar, 1);
+        mbar_init(t_bar, 128);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<128>(bars + 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tslot;
+    const int ldq = 3 * p.heads * kHeadDim;
+    const long long ldo = static_cast<long long>(p.heads) * kHeadDim;
+
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, phase ^= 1u) {
+        const int b = item / p.heads, h = item - b * p.heads;
+        int off, len;
+        if (p.seq_off) {
+            off = __ldg(p.seq_off + b);
+            len = __ldg(p.seq_off + b + 1) - off;
+        } else {
+            off = b * p.S_max;
+            len = p.S_max;
+        }
+        len = len > 128 ? 128 : len;
+        const int n16 = len > 0 ? (len + 15) & ~15 : 16;  // keys rounded up to the MMA granule
+
+        if (warp == 4) {
+            // ------------------------------------------------ control: TMA + MMA issue
+            if (lane == 0) {
+                if (item != static_cast<int>(blockIdx.x)) mbar_wait(o_bar, phase ^ 1u);  // smem of the previous item consumed
+                mbar_expect_tx(full_bar, 3u * 16384u);
+                tma_load_2d(&p.qkv_map, full_bar, q_s, h * kHeadDim, off);
+                tma_load_2d(&p.qkv_map, full_bar, k_s, (p.heads + h) * kHeadDim, off);
+                tma_load_2d(&p.qkv_map, full_bar, v_s, (2 * p.heads + h) * kHeadDim, off);
+                mbar_wait(full_bar, phase);
+                if (item != static_cast<int>(blockIdx.x)) mbar_wait(t_bar, phase ^ 1u);  // O of the previous item read out
+                tc_fence_after();
+                {   // S[128 x n16] = Q K^T
+                    const uint32_t idesc = make_idesc_bf16(128, n16, 0, 0);
+                    const uint64_t adesc = make_smem_desc(q_s, 0, 1024, 2);
+                    const uint64_t bdesc = make_smem_desc(k_s, 0, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(tm, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+                    umma_commit(s_bar);
+                }
+                mbar_wait(p_bar, phase);
+                tc_fence_after();
+                {   // O[128 x 64] = P[128 x n16] V[n16 x 64]; V rows are keys: MN-major B, 2 KB per 16 keys
+                    const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+                    for (int k = 0; k < n16 / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc(q_s + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, 2);
+                        const uint64_t bdesc = make_smem_desc(v_s + k * 2048, 0, 1024, 2);
+                        umma_bf16(tm, adesc, bdesc, idesc, k != 0);
+                    }
+                    umma_commit(o_bar);
+                }
+            }
+            __syncwarp();
+        } else {
+            // ------------------------------------------------ softmax warps: thread = query row
+            const int row = tid;  // 0..127 == TMEM lane
+            bias_s[row] = row < len ? (p.bias ? __ldg(p.bias + off + row) : 0.0f) : -INFINITY;
+            named_bar_sync(1, 128);
+            const uint32_t t_row = tm + (static_cast<uint32_t>(warp * 32) << 16);
+            mbar_wait(s_bar, phase);
+            tc_fence_after();
+            // pass 1: row maximum over the attended keys
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < n16; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) + bias_s[c0 + j]);
+            }
+            const float ms = (mx == -INFINITY ? 0.0f : mx) * kLog2e;
+            // pass 2: probabilities -> bf16 A operand (K-major, two 64-key swizzle atoms over Q|K)
+            float sum = 0.0f;
+            for (int c0 = 0; c0 < n16; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c0, v);
+                tmem_ld_wait();
+                float e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    e[j] = fast_exp2(fmaf(__uint_as_float(v[j]) + bias_s[c0 + j], kLog2e, -ms));
+                    sum += e[j];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (c0 + q * 8 >= n16) break;
+                    uint4 o;
+                    o.x = pack_bf16(e[q * 8 + 0], e[q * 8 + 1]);
+                    o.y = pack_bf16(e[q * 8 + 2], e[q * 8 + 3]);
+                    o.z = pack_bf16(e[q * 8 + 4], e[q * 8 + 5]);
+                    o.w = pack_bf16(e[q * 8 + 6], e[q * 8 + 7]);
+                    const int c8 = (c0 >> 3) + q;  // 8-key chunk index 0..15
+                    *reinterpret_cast<uint4*>(gen + (c8 >> 3) * 16384 + row * 128 + (((c8 & 7) ^ (row & 7)) << 4)) = o;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_bar);
+            // O row back from TMEM, normalise, store
+            mbar_wait(o_bar, phase);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(t_row, o0);
+            tmem_ld32(t_row + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(t_bar);
+            if (row < len) {
+                const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(off) + row) * ldo + h * kHeadDim);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(o0[q * 8 + 0]) * inv, __uint_as_float(o0[q * 8 + 1]) * inv);
+                    w.y = pack_bf16(__uint_as_float(o0[q * 8 + 2]) * inv, __uint_as_float(o0[q * 8 + 3]) * inv);
+                    w.z = pack_bf16(__uint_as_float(o0[q * 8 + 4]) * inv, __uint_as_float(o0[q * 8 + 5]) * inv);
+                    w.w = pack_bf16(__uint_as_float(o0[q * 8 + 6]) * inv, __uint_as_float(o0[q * 8 + 7]) * inv);
+                    dst[q] = w;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(o1[q * 8 + 0]) * inv, __uint_as_float(o1[q * 8 + 1]) * inv);
+                    w.y = pack_bf16(__uint_as_float(o1[q * 8 + 2]) * inv, __uint_as_float(o1[q * 8 + 3]) * inv);
+                    w.z = pack_bf16(__uint_as_float(o1[q * 8 + 4]) * inv, __uint_as_float(o1[q * 8 + 5]) * inv);
+                    w.w = pack_bf16(__uint_as_float(o1[q * 8 + 6]) * inv, __uint_as_float(o1[q * 8 + 7]) * inv);
+                    dst[4 + q] = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<128>(tm);
+    }
+}
+
+int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
+              int heads, long long rows_alloc, __nv_bfloat16* out, cudaStream_t stream) {
+    constexpr int SMEM = 49152 + 1024 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) {
+            set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return -static_cast<int>(e);
+        }
+        attr_set = true;
+    }
+    TcParams p;
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * heads * kHeadDim, static_cast<uint64_t>(rows_alloc)};
+    uint64_t str[1] = {static_cast<uint64_t>(3) * heads * kHeadDim * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = encode_tensor_map(&p.qkv_map, qkv, 2, 2, dims, str, box, 128);
+    if (rc) return rc;
+    p.bias = mask_bias;
+    p.seq_off = seq_off;
+    p.out = out;
+    p.S_max = S;
+    p.heads = heads;
+    p.items = B * heads;
+    const int grid = p.items < 148 * 4 ? p.items : 148 * 4;
+    attention_tc_kernel<<<grid, kTcThreads, SMEM, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("attention_tc_kernel launch: %s", cudaGetErrorString(e));
+        return -static_cast<int>(e);
+    }
+    return 0;
+}
+
 }  // namespace
 
+void attention_set_tc(bool on) { g_attention_tc = on; }
+
 int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
-                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream) {
+                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc) {
     if (B <= 0 || S <= 0) return 0;
     if (S > kMaxS || heads <= 0 || heads > 65535 || B > 65535) {
         set_last_error("attention_forward: unsupported B=%d S=%d heads=%d (S <= %d)", B, S, heads,
@@ -369,6 +589,10 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     }
     // 64-row query blocks when sequences are short (or packed to short lengths): a block whose rows
     // all lie beyond the sequence exits immediately; 128-row blocks halve the K/V re-reads otherwise
+    // whole sequences fit one 128x128 tile: tcgen05 path (rows_alloc bounds the TMA view of qkv)
+    if (S <= 128 && g_attention_tc && static_cast<long long>(B) * heads < 0x7fffffffLL)
+        return launch_tc(qkv, mask_bias, seq_off, B, S, heads,
+                         rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, out, stream);
     if (S > 64)
         return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
     return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);

@@ -649,6 +649,10 @@ int ensure_text_ws(mrd_ctx* c, int tokens) {
     c->t_scratch = arena_take<int>(&c->text_ws, T + 2);
     c->t_nrows = arena_take<int>(&c->text_ws, 1);
     c->text_ws_tokens = tokens;
+    // rows beyond the live token count are read (never used) by tile-granular kernels: keep every
+    // byte of the workspace a finite number from the start
+    cudaError_t e = cudaMemset(c->text_ws.base, 0, c->text_ws.bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(text workspace)");
     return 0;
 }
 
@@ -933,7 +937,7 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
             {
                 ProfScope ps(c, s, "bert.attention", CAT_ATTN, attn_flops, 1.0 * T * Hd * 2 * 4);
                 MRD_TRY(attention_forward(c->t_qkv, c->t_bias, c->t_seq_off, nb, S, c->bert_heads,
-                                          c->t_ctx, s));
+                                          c->t_ctx, s, c->text_ws_tokens));
             }
             MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
             {

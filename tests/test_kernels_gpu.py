@@ -265,6 +265,14 @@ def test_bert_embed(lib, cuda):
 
 
 # ------------------------------------------------------------------ attention (K3)
+@pytest.fixture(params=["tcgen05", "mma.sync"])
+def attn_path(request, lib):
+    """S <= 128 has two implementations: run the attention tests through both."""
+    lib.mrd_attention_use_tcgen05(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    lib.mrd_attention_use_tcgen05(1)
+
+
 @pytest.mark.parametrize("B,S,heads,lengths", [
     (2, 128, 12, None),
     (3, 128, 12, [128, 70, 1]),
@@ -272,7 +280,7 @@ def test_bert_embed(lib, cuda):
     (3, 48, 4, [48, 33, 5]),       # S < 64: BLOCK_M = 64 path, ragged
     (2, 200, 12, [200, 129]),      # S not a multiple of 64
 ])
-def test_attention(lib, cuda, B, S, heads, lengths):
+def test_attention(lib, cuda, attn_path, B, S, heads, lengths):
     g = torch.Generator(device="cuda").manual_seed(S + B)
     D = heads * 64
     qkv = torch.randn(B * S, 3 * D, device=cuda, generator=g).to(BF)
@@ -337,8 +345,9 @@ def test_compact_tokens(lib, cuda, B, S, keep_all):
     assert torch.equal(row_bias[:n], want_bias.float())
 
 
-@pytest.mark.parametrize("lens,heads", [([128, 70, 1, 64, 65], 12), ([512, 64, 300], 12), ([5, 48, 33], 4)])
-def test_attention_varlen(lib, cuda, lens, heads):
+@pytest.mark.parametrize("lens,heads", [([128, 70, 1, 64, 65], 12), ([512, 64, 300], 12), ([5, 48, 33], 4),
+                                        ([17] * 700, 12)])
+def test_attention_varlen(lib, cuda, attn_path, lens, heads):
     g = torch.Generator(device="cuda").manual_seed(sum(lens))
     B, D, T = len(lens), heads * 64, sum(lens)
     qkv = torch.randn(T, 3 * D, device=cuda, generator=g).to(BF)
@@ -348,7 +357,7 @@ def test_attention_varlen(lib, cuda, lens, heads):
     bias[seq_off[1].item()] = float("-inf")   # a kept-but-masked CLS row (sample 1)
     out = torch.full((T, D), float("nan"), device=cuda, dtype=BF)
     _check(lib, lib.mrd_attention_varlen_bf16(qkv.data_ptr(), bias.data_ptr(), seq_off.data_ptr(), B,
-                                              max(lens), heads, out.data_ptr(), _stream()))
+                                              max(lens), heads, T, out.data_ptr(), _stream()))
     torch.cuda.synchronize()
     for b, L in enumerate(lens):
         o = int(seq_off[b])
