@@ -373,7 +373,7 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off,
 constexpr int kTcThreads = 160;
 
 struct TcParams {
-    CUtensorMap qkv_map;
+    CUtensorMap qkv_map[4];  // boxes of 32 / 64 / 96 / 128 rows: fetch only the rows the sample has
     const float* bias;     // per row (packed) or [B,S] (dense); may be null
     const int* seq_off;    // packed layout or null
     __nv_bfloat16* out;
@@ -392,8 +392,12 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
     volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + 49152 + 512 + 64);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // rows a short sample does not fetch keep whatever the previous item left there (finite values
+    // that are masked or multiplied by zero); make the very first contents finite as well
+    for (int i = tid; i < 49152 / 16; i += kTcThreads) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     if (tid == 0) {
-        tma_prefetch_desc(&p.qkv_map);
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.qkv_map[i]);
         mbar_init(full_bar, 1);
         mbar_init(s_bar, 1);
         mbar_init(p_bar, 128);
@@ -406,7 +410,6 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tslot;
-    const int ldq = 3 * p.heads * kHeadDim;
     const long long ldo = static_cast<long long>(p.heads) * kHeadDim;
 
     uint32_t phase = 0;
@@ -427,10 +430,12 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
             // ------------------------------------------------ control: TMA + MMA issue
             if (lane == 0) {
                 if (item != static_cast<int>(blockIdx.x)) mbar_wait(o_bar, phase ^ 1u);  // smem of the previous item consumed
-                mbar_expect_tx(full_bar, 3u * 16384u);
-                tma_load_2d(&p.qkv_map, full_bar, q_s, h * kHeadDim, off);
-                tma_load_2d(&p.qkv_map, full_bar, k_s, (p.heads + h) * kHeadDim, off);
-                tma_load_2d(&p.qkv_map, full_bar, v_s, (2 * p.heads + h) * kHeadDim, off);
+                const int bi = (len - 1) >> 5;  // box of 32 * (bi + 1) rows
+                const CUtensorMap* map = &p.qkv_map[bi];
+                mbar_expect_tx(full_bar, 3u * 4096u * static_cast<uint32_t>(bi + 1));
+                tma_load_3d(map, full_bar, q_s, 0, off, h);
+                tma_load_3d(map, full_bar, k_s, 0, off, p.heads + h);
+                tma_load_3d(map, full_bar, v_s, 0, off, 2 * p.heads + h);
                 mbar_wait(full_bar, phase);
                 if (item != static_cast<int>(blockIdx.x)) mbar_wait(t_bar, phase ^ 1u);  // O of the previous item read out
                 tc_fence_after();
@@ -542,7 +547,7 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
 }
 
 int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
-              int heads, long long rows_alloc, __nv_bfloat16* out, cudaStream_t stream) {
+              int heads, long long rows_alloc, int blocked, __nv_bfloat16* out, cudaStream_t stream) {
     constexpr int SMEM = 49152 + 1024 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -554,11 +559,17 @@ int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_o
         attr_set = true;
     }
     TcParams p;
-    uint64_t dims[2] = {static_cast<uint64_t>(3) * heads * kHeadDim, static_cast<uint64_t>(rows_alloc)};
-    uint64_t str[1] = {static_cast<uint64_t>(3) * heads * kHeadDim * 2};
-    uint32_t box[2] = {64, 128};
-    int rc = encode_tensor_map(&p.qkv_map, qkv, 2, 2, dims, str, box, 128);
-    if (rc) return rc;
+    // 3-D view {64 dims, rows, 3*heads column blocks}: token-major rows are 3*heads*64 elements apart
+    // with the blocks side by side; in the blocked layout every block is a contiguous [rows,64] matrix
+    const uint64_t nblk = static_cast<uint64_t>(3) * heads;
+    uint64_t dims[3] = {64, static_cast<uint64_t>(rows_alloc), nblk};
+    uint64_t str_tok[2] = {nblk * 128, 128};
+    uint64_t str_blk[2] = {128, static_cast<uint64_t>(rows_alloc) * 128};
+    for (int i = 0; i < 4; ++i) {
+        uint32_t box[3] = {64, static_cast<uint32_t>(32 * (i + 1)), 1};
+        int rc = encode_tensor_map(&p.qkv_map[i], qkv, 2, 3, dims, blocked ? str_blk : str_tok, box, 128);
+        if (rc) return rc;
+    }
     p.bias = mask_bias;
     p.seq_off = seq_off;
     p.out = out;
@@ -579,9 +590,16 @@ int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_o
 
 void attention_set_tc(bool on) { g_attention_tc = on; }
 
+bool attention_prefers_blocked_qkv(int S) { return S <= 128 && g_attention_tc; }
+
 int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
-                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc) {
+                      int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc,
+                      int blocked) {
     if (B <= 0 || S <= 0) return 0;
+    if (blocked && !(S <= 128 && g_attention_tc)) {
+        set_last_error("attention_forward: the blocked qkv layout is only read by the tcgen05 path (S <= 128)");
+        return -1;
+    }
     if (S > kMaxS || heads <= 0 || heads > 65535 || B > 65535) {
         set_last_error("attention_forward: unsupported B=%d S=%d heads=%d (S <= %d)", B, S, heads,
                        kMaxS);
@@ -592,7 +610,7 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     // whole sequences fit one 128x128 tile: tcgen05 path (rows_alloc bounds the TMA view of qkv)
     if (S <= 128 && g_attention_tc && static_cast<long long>(B) * heads < 0x7fffffffLL)
         return launch_tc(qkv, mask_bias, seq_off, B, S, heads,
-                         rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, out, stream);
+                         rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream);
     if (S > 64)
         return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
     return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);

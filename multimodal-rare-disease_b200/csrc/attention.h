@@ -16,7 +16,10 @@ namespace mrd {
 // S <= 128 runs on tcgen05 (TMA-fed 128x128 tiles, S and O in TMEM); longer sequences on mma.sync.
 int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
                       int S, int heads, __nv_bfloat16* out, cudaStream_t stream,
-                      long long rows_alloc = 0);
+                      long long rows_alloc = 0, int blocked = 0);
+// blocked = 1: qkv is [3*heads][rows_alloc][64] (what plan_gemm(c_blocked=1) writes): each head's Q, K
+// and V tile is one contiguous block - streaming-friendly for the TMA loads of the tcgen05 path.
+bool attention_prefers_blocked_qkv(int S);
 // test hook: force the mma.sync path for every S
 void attention_set_tc(bool on);
 

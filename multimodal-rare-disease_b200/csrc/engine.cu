@@ -80,6 +80,7 @@ struct CnnPlan {
 
 struct TextPlan {
     int B = 0, S = 0;
+    int blocked_qkv = 0;  // QKV written as [36][T][64] for the tcgen05 attention (S <= 128)
     struct LayerPlan {
         GemmLaunch qkv, o, f1, f2;
     };
@@ -666,12 +667,13 @@ int get_text_plan(mrd_ctx* c, int B, int S, TextPlan** out) {
     TextPlan p;
     p.B = B; p.S = S;
     const int T = B * S, Hd = c->hidden;
+    p.blocked_qkv = attention_prefers_blocked_qkv(S) ? 1 : 0;
     p.layers.resize(c->layers.size());
     for (size_t i = 0; i < c->layers.size(); ++i) {
         const BertLayerW& L = c->layers[i];
         TextPlan::LayerPlan& lp = p.layers[i];
         MRD_TRY(plan_gemm(&lp.qkv, c->t_h, Hd, T, Hd, L.qkv.w, 3 * Hd, L.qkv.b, c->t_qkv, 3 * Hd,
-                          nullptr, 0, nullptr, 0, ACT_NONE));
+                          nullptr, 0, nullptr, 0, ACT_NONE, p.blocked_qkv));
         MRD_TRY(plan_gemm(&lp.o, c->t_ctx, Hd, T, Hd, L.o.w, Hd, L.o.b, c->t_tmp, Hd, c->t_h, Hd,
                           nullptr, 0, ACT_NONE));
         MRD_TRY(plan_gemm(&lp.f1, c->t_h2, Hd, T, Hd, L.f1.w, c->ffn, L.f1.b, c->t_ffn, c->ffn,
@@ -936,8 +938,10 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
             MRD_TRY(run(c, "bert.qkv", lp.qkv, s));
             {
                 ProfScope ps(c, s, "bert.attention", CAT_ATTN, attn_flops, 1.0 * T * Hd * 2 * 4);
+                // blocked layout: block stride = the M the QKV plan was built with (T rows)
                 MRD_TRY(attention_forward(c->t_qkv, c->t_bias, c->t_seq_off, nb, S, c->bert_heads,
-                                          c->t_ctx, s, c->text_ws_tokens));
+                                          c->t_ctx, s, p->blocked_qkv ? T : c->text_ws_tokens,
+                                          p->blocked_qkv));
             }
             MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
             {

@@ -470,8 +470,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             fence_proxy_async_smem();
             named_bar_sync(1, kEpiThreads);
             if (epi_tid == 0 && p.store_bf16) {
-                tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, t.n_idx * BLOCK_N + sub * 64,
-                             t.w0, t.h0, t.n0);
+                if (p.c_blocked)
+                    tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, 0, t.w0, t.n_idx * NSUB + sub, 0);
+                else
+                    tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, t.n_idx * BLOCK_N + sub * 64,
+                                 t.w0, t.h0, t.n0);
                 tma_store_commit();
             }
         }
@@ -600,7 +603,7 @@ int gemm_num_sms() {
 int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
               const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* Cout, long long ldc,
               const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
-              int act) {
+              int act, int c_blocked) {
     memset(g, 0, sizeof(*g));
     if (M <= 0 || K <= 0 || N <= 0 || K % 64 != 0 || N % 64 != 0 || lda % 8 != 0 ||
         (Cout && ldc % 8 != 0)) {
@@ -642,7 +645,14 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
         int rc = encode_tensor_map(&p.b_map, W, 2, 2, dims, str, box, 128);
         if (rc) return rc;
     }
-    if (Cout) {
+    p.c_blocked = (Cout && c_blocked) ? 1 : 0;
+    if (Cout && c_blocked) {
+        uint64_t dims[4] = {64, (uint64_t)M, (uint64_t)(N / 64), 1};
+        uint64_t str[3] = {128, (uint64_t)M * 128, (uint64_t)M * 128 * (N / 64)};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_tensor_map(&p.c_map, Cout, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    } else if (Cout) {
         uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, 1, 1};
         uint64_t str[3] = {(uint64_t)ldc * 2, (uint64_t)ldc * 2 * M, (uint64_t)ldc * 2 * M};
         uint32_t box[4] = {64, 128, 1, 1};

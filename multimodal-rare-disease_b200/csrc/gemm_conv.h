@@ -32,6 +32,7 @@ struct alignas(64) ConvGemmParams {
     long long ld_f32;               // out_f32 row stride in elements
     const int* dyn_rows;            // optional (device): live GEMM rows <= M; tiles beyond are skipped
     int has_res;                    // 1: add the residual tile fetched through r_map
+    int c_blocked;                  // 1: C is stored as [N/64][M][64] (one contiguous block per 64 columns)
     int stages, ring;               // operand pipeline depth, residual ring depth (16 KB sub-tiles)
     int w_shift;                    // added to the tile's first column (flat 3x3 mode: -1)
     int span_rows, a_stage_bytes, b_res_bytes;  // weights-resident modes: halo span rows, A stage / weight panel bytes
@@ -59,10 +60,12 @@ struct GemmLaunch {
 
 // Plain GEMM.  A: [M,K] bf16 with row stride lda; W: [N,K] bf16 (nn.Linear layout); C: [M,N] bf16
 // with row stride ldc (may be null when only out_f32 is wanted).  K % 64 == 0, N % 64 == 0.
+// c_blocked = 1: C is written as [N/64][M][64] instead of row-major [M][N] (ldc ignored): every
+// 64-column block (one attention head of Q, K or V) becomes one contiguous [M,64] matrix.
 int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K,
               const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* C, long long ldc,
               const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
-              int act);
+              int act, int c_blocked = 0);
 
 // ksize in {1,3}, stride in {1,2}, padding = ksize/2.  X: [N,H,W,Cin] bf16, Wt: [Cout][k][k][Cin]
 // bf16 (BN already folded), Y: [N,H/stride,W/stride,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0.
