@@ -85,6 +85,9 @@ struct TextPlan {
         GemmLaunch qkv, o, f1, f2;
     };
     std::vector<LayerPlan> layers;
+    // last layer, CLS rows only (M = B): everything after its attention feeds nothing but the CLS row
+    // (src/text_encoder.py:118), so the out-projection, both LayerNorms and the FFN run on B rows
+    GemmLaunch o_cls, f1_cls, f2_cls;
 };
 
 struct BatchPlan {
@@ -160,7 +163,7 @@ struct mrd_ctx {
     };
     Arena cnn_ws, text_ws, batch_ws;
     int cnn_ws_B = 0, cnn_ws_H = 0, cnn_ws_W = 0;
-    int text_ws_tokens = 0;
+    int text_ws_tokens = 0, text_ws_seqs = 0;
     int batch_ws_B = 0;
 
     // cnn chunk buffers
@@ -174,6 +177,8 @@ struct mrd_ctx {
     // text chunk buffers
     bf16 *t_h = nullptr, *t_h2 = nullptr, *t_qkv = nullptr, *t_ctx = nullptr, *t_tmp = nullptr,
          *t_ffn = nullptr;
+    bf16 *t_cls_ctx = nullptr, *t_cls_h = nullptr, *t_cls_h2 = nullptr, *t_cls_tmp = nullptr,
+         *t_cls_ffn = nullptr;  // CLS-row tail of the last layer
     float* t_bias = nullptr;   // key bias per packed row
     int *t_seq_off = nullptr, *t_row_tok = nullptr, *t_nrows = nullptr, *t_scratch = nullptr;
     // batch buffers
@@ -630,13 +635,17 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
     return 0;
 }
 
-int ensure_text_ws(mrd_ctx* c, int tokens) {
-    if (c->text_ws.base && c->text_ws_tokens >= tokens) return 0;
+int ensure_text_ws(mrd_ctx* c, int tokens, int seqs) {
+    if (c->text_ws.base && c->text_ws_tokens >= tokens && c->text_ws_seqs >= seqs) return 0;
     c->text_plans.clear();
+    if (tokens < c->text_ws_tokens) tokens = c->text_ws_tokens;
+    if (seqs < c->text_ws_seqs) seqs = c->text_ws_seqs;
+    c->text_ws_seqs = seqs;
     const long long T = tokens;
     const int Hd = c->hidden;
+    const long long Sq = c->text_ws_seqs;  // most sequences one pass can hold
     size_t total = 4 * pad1k(T * Hd, 2) + pad1k(T * 3 * Hd, 2) + pad1k(T * c->ffn, 2) +
-                   4 * pad1k(T + 2, 4) + pad1k(1, 4);
+                   4 * pad1k(T + 2, 4) + pad1k(1, 4) + 4 * pad1k(Sq * Hd, 2) + pad1k(Sq * c->ffn, 2);
     MRD_TRY(arena_reset(c, &c->text_ws, total));
     c->t_h = arena_take<bf16>(&c->text_ws, T * Hd);
     c->t_h2 = arena_take<bf16>(&c->text_ws, T * Hd);
@@ -644,6 +653,11 @@ int ensure_text_ws(mrd_ctx* c, int tokens) {
     c->t_tmp = arena_take<bf16>(&c->text_ws, T * Hd);
     c->t_qkv = arena_take<bf16>(&c->text_ws, T * 3 * Hd);
     c->t_ffn = arena_take<bf16>(&c->text_ws, T * c->ffn);
+    c->t_cls_ctx = arena_take<bf16>(&c->text_ws, Sq * Hd);
+    c->t_cls_h = arena_take<bf16>(&c->text_ws, Sq * Hd);
+    c->t_cls_h2 = arena_take<bf16>(&c->text_ws, Sq * Hd);
+    c->t_cls_tmp = arena_take<bf16>(&c->text_ws, Sq * Hd);
+    c->t_cls_ffn = arena_take<bf16>(&c->text_ws, Sq * c->ffn);
     c->t_bias = arena_take<float>(&c->text_ws, T + 2);
     c->t_seq_off = arena_take<int>(&c->text_ws, T + 2);
     c->t_row_tok = arena_take<int>(&c->text_ws, T + 2);
@@ -682,6 +696,15 @@ int get_text_plan(mrd_ctx* c, int B, int S, TextPlan** out) {
                           c->t_h2, Hd, nullptr, 0, ACT_NONE));
         // rows are token-packed: the live count is produced on the device by compact_tokens
         lp.qkv.p.dyn_rows = lp.o.p.dyn_rows = lp.f1.p.dyn_rows = lp.f2.p.dyn_rows = c->t_nrows;
+    }
+    {
+        const BertLayerW& L = c->layers.back();
+        MRD_TRY(plan_gemm(&p.o_cls, c->t_cls_ctx, Hd, B, Hd, L.o.w, Hd, L.o.b, c->t_cls_tmp, Hd,
+                          c->t_cls_h, Hd, nullptr, 0, ACT_NONE));
+        MRD_TRY(plan_gemm(&p.f1_cls, c->t_cls_h2, Hd, B, Hd, L.f1.w, c->ffn, L.f1.b, c->t_cls_ffn,
+                          c->ffn, nullptr, 0, nullptr, 0, ACT_GELU));
+        MRD_TRY(plan_gemm(&p.f2_cls, c->t_cls_ffn, c->ffn, B, c->ffn, L.f2.w, Hd, L.f2.b,
+                          c->t_cls_tmp, Hd, c->t_cls_h2, Hd, nullptr, 0, ACT_NONE));
     }
     auto ins = c->text_plans.emplace(key, std::move(p));
     *out = &ins.first->second;
@@ -905,7 +928,7 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
     int seqs = c->tok_chunk / S;
     if (seqs < 1) seqs = 1;
     if (seqs > B) seqs = B;
-    MRD_TRY(ensure_text_ws(c, seqs * S));
+    MRD_TRY(ensure_text_ws(c, seqs * S, seqs));
     static const size_t msz[5] = {8, 4, 4, 1, 2};
     const int Hd = c->hidden;
     for (int b0 = 0; b0 < B; b0 += seqs) {
@@ -943,6 +966,35 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                                           c->t_ctx, s, p->blocked_qkv ? T : c->text_ws_tokens,
                                           p->blocked_qkv));
             }
+            if (i + 1 == p->layers.size() && !last_hidden) {
+                // ---- last layer: only the CLS row of each sequence is consumed downstream
+                {
+                    ProfScope ps(c, s, "gather_cls", CAT_MEM, 0, 8.0 * nb * Hd);
+                    MRD_TRY(gather_cls_rows(c->t_ctx, c->t_seq_off, nb, Hd, c->t_cls_ctx, nullptr, s));
+                    MRD_TRY(gather_cls_rows(c->t_h, c->t_seq_off, nb, Hd, c->t_cls_h, nullptr, s));
+                    ++c->launches;
+                }
+                MRD_TRY(run(c, "bert.cls.attn_out+res", p->o_cls, s));
+                {
+                    ProfScope ps(c, s, "bert.cls.layernorm", CAT_MEM, 0, 4.0 * nb * Hd);
+                    MRD_TRY(layernorm_residual(c->t_cls_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b,
+                                               c->bert_ln_eps, nb, Hd, c->t_cls_h2, Hd, nullptr, 0, s));
+                }
+                MRD_TRY(run(c, "bert.cls.ffn1+gelu", p->f1_cls, s));
+                MRD_TRY(run(c, "bert.cls.ffn2+res", p->f2_cls, s));
+                {
+                    ProfScope ps(c, s, "bert.cls.layernorm", CAT_MEM, 0, 4.0 * nb * Hd);
+                    MRD_TRY(layernorm_residual(c->t_cls_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b,
+                                               c->bert_ln_eps, nb, Hd, c->b_txt + 1LL * b0 * Hd, Hd,
+                                               nullptr, 0, s));
+                }
+                if (cls_f32) {
+                    ProfScope ps(c, s, "cls_to_f32", CAT_MEM, 0, 6.0 * nb * Hd);
+                    MRD_TRY(cast_bf16_to_f32(c->b_txt + 1LL * b0 * Hd, Hd, nb, Hd,
+                                             cls_f32 + 1LL * b0 * Hd, Hd, s));
+                }
+                break;
+            }
             MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
             {
                 ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
@@ -957,8 +1009,9 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                                            Hd, c->t_h, Hd, nullptr, 0, s, c->t_nrows));
             }
         }
-        // CLS rows (src/text_encoder.py:118): the first packed row of every sequence
-        {
+        if (last_hidden) {
+            // full last layer was computed: CLS rows (src/text_encoder.py:118) = first packed row of
+            // every sequence
             ProfScope ps(c, s, "gather_cls", CAT_MEM, 0, 8.0 * nb * Hd);
             MRD_TRY(gather_cls_rows(c->t_h, c->t_seq_off, nb, Hd, c->b_txt + 1LL * b0 * Hd,
                                     cls_f32 ? cls_f32 + 1LL * b0 * Hd : nullptr, s));

@@ -252,3 +252,21 @@ def test_forward_host_streams_match_device_forward(cuda, state):
     torch.cuda.synchronize()
     assert torch.equal(out["logits"], ref["logits"]) and torch.equal(out["probs"], ref["probs"])
     assert torch.equal(out2["logits"], _fwd(model, images, ids, None)["logits"])
+
+
+def test_cls_tail_matches_full_last_layer(cuda, state):
+    """forward() runs the last BERT layer on the CLS rows only (token-packed, M = B);
+    get_last_hidden_state() keeps every token and runs the full layer.  Row 0 must agree exactly."""
+    model = _use(state, "sens")
+    _, ids, mask = synth.make_inputs(6, 48, 31, [48, 20, 1, 33, 48, 7], H=32, W=32)
+    with torch.no_grad():
+        cls = model.text_encoder(ids.cuda(), mask.cuda())
+        last = model.text_encoder.get_last_hidden_state(ids.cuda(), mask.cuda())
+    assert last.shape == (6, 48, 768)
+    assert torch.equal(cls, last[:, 0, :])
+    sd = {k: v.float() for k, v in state["sens"].items() if v.is_floating_point()}
+    with torch.no_grad():
+        ref = oracle.bert_encoder(sd, ids, mask)
+    # attended positions of the full hidden state match the oracle too (padded rows are unspecified)
+    for b, L in enumerate([48, 20, 1, 33, 48, 7]):
+        assert _rel_rows(last[b, :L], ref[b, :L]) <= REL_TOL
