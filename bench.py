@@ -95,6 +95,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the
+    committed ncu capture of this same command (profiles/r01_traffic.json); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh)
+
+
 def make_shard(n, seed, device=None, pin=False):
     """This rank's synthetic shard (SURVEY.md 8(d) cfg 4): randn images, ids with [CLS] first and 0 on
     the padded tail, prefix masks with L ~ U{16..128}."""
@@ -187,10 +197,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    if os.environ.get("MRD_BENCH_WATCHDOG"):  # dump all stacks and exit instead of hanging a GPU box
-        import faulthandler
+    # dump all stacks and exit instead of hanging a GPU box (a healthy run takes 1-2 minutes)
+    import faulthandler
 
-        faulthandler.dump_traceback_later(int(os.environ["MRD_BENCH_WATCHDOG"]), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("MRD_BENCH_WATCHDOG", "1500")), exit=True)
     import torch
     import torch.distributed as dist
 
@@ -249,6 +259,8 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - l0
     clocks = sampler.stop() if sampler else None
+    # tokens the packed BERT path actually processes (mask != 0, CLS always kept) vs the dense count
+    live_frac = float(((mask != 0) | (torch.arange(SEQ, device=dev) == 0)).float().mean().item())
     t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
@@ -313,7 +325,11 @@ def main():
                     "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["src"] + " (sustained: timed inside a long step)",
                     "launches_per_step": n_l, "avg_launch_ms": t_ms / max(n_l, 1),
                     "flops_per_launch_avg": t_fl / max(n_l, 1), "share_of_step": t_ms / all_ms if all_ms else None,
-                    "traffic": None}
+                    "traffic": _ncu_traffic(),
+                    "note": "achieved counts ALGORITHMIC flops (dense, as the reference executes; SURVEY 8(d)). "
+                            f"The BERT launches skip padded tokens (live fraction {live_frac:.3f} of B*S) and the last "
+                            "layer's post-attention half runs on CLS rows only, so executed FLOP/s are lower: "
+                            "see profiles/ and DESIGN.md section 5."}
         fam = {}
         for r in rows:
             f = fam.setdefault(r["cat"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
@@ -348,7 +364,7 @@ def main():
             "tensor_peak_frac": value * FLOP_PER_SAMPLE / (world * peaks["bf16_burst"] * 1e12),
             "tensor_peak_tflops": peaks["bf16_burst"], "flop_per_sample": FLOP_PER_SAMPLE,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "kernel_families": families, "cpu_baseline": cpu,
+            "kernel_families": families, "cpu_baseline": cpu, "bert_live_token_fraction": live_frac,
             "device_bytes": eng.device_bytes,
         }
         print(json.dumps(line))
