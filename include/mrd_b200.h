@@ -78,9 +78,11 @@ int mrd_cnn_encoder_fwd(mrd_ctx* ctx, const void* images, int img_dtype, int B, 
  * hidden state (eval mode, pooler skipped: its output is unused with use_pooler_output=False).
  * ids: i64 [B,S]; mask: [B,S] of mask_dtype, key j of sample b is attended iff mask[b,j] != 0
  * (HF:masking_utils.py:1001-1088); mask may be NULL (= all ones).  cls: f32 [B,768].
- * last_hidden (optional): f32 [B,S,768]. */
+ * last_hidden (optional): f32 [B,S,768]; requesting it keeps every token (no packing) so padded rows
+ * are computed as the reference computes them.  all_hidden (optional, needs last_hidden): f32
+ * [layers+1,B,S,768], HF's hidden_states tuple (src/text_encoder.py:129-149). */
 int mrd_text_encoder_fwd(mrd_ctx* ctx, const long long* ids, const void* mask, int mask_dtype, int B,
-                         int S, float* cls, float* last_hidden, void* stream);
+                         int S, float* cls, float* last_hidden, float* all_hidden, void* stream);
 
 /* MultimodalFusion.forward with fusion_type="attention" (src/fusion_model.py:245-291).
  * img_emb f32 [B,Di], txt_emb f32 [B,Dt] -> fused f32 [B,Hd].  attn_i2t / attn_t2i (optional):

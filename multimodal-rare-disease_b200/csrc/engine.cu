@@ -916,7 +916,7 @@ int run_projection(mrd_ctx* c, BatchPlan* bp, float* emb_f32, cudaStream_t s) {
 
 // BERT encoder over the whole batch in micro-batches; leaves CLS rows in b_txt (+ optional fp32).
 int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype, int B, int S,
-             float* cls_f32, float* last_hidden, cudaStream_t s) {
+             float* cls_f32, float* last_hidden, float* all_hidden, cudaStream_t s) {
     if (!c->has_text) {
         set_last_error("text_encoder weights are not loaded in this context");
         return -3;
@@ -940,7 +940,19 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                              : nullptr;
         // token packing: padded positions are dropped (they influence nothing TextEncoder.forward
         // returns); every later kernel reads the live row count from the device, so no host sync
+        if (all_hidden && !last_hidden) {
+            set_last_error("all_hidden requires last_hidden (both keep every token)");
+            return -1;
+        }
         const int keep_all = last_hidden != nullptr;
+        // hidden_states[l] of HF BertModel: l = 0 is the embedding output, l = i+1 the output of layer i;
+        // layout [L+1, B, S, Hd] fp32 (src/text_encoder.py:129-149)
+        auto export_hidden = [&](size_t l) -> int {
+            if (!all_hidden) return 0;
+            ProfScope ps(c, s, "hidden_to_f32", CAT_MEM, 0, 6.0 * T * Hd);
+            return cast_bf16_to_f32(c->t_h, Hd, T, Hd,
+                                    all_hidden + (static_cast<long long>(l) * B + b0) * S * Hd, Hd, s);
+        };
         {
             ProfScope ps(c, s, "compact_tokens", CAT_MEM, 0, 1.0 * T * (msz[mask_dtype] + 8));
             MRD_TRY(compact_tokens(m, mask_dtype, nb, S, keep_all, c->t_seq_off, c->t_row_tok,
@@ -953,6 +965,7 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                                          c->emb_b, c->bert_ln_eps, c->vocab, c->t_h, s, c->t_row_tok,
                                          c->t_nrows));
         }
+        MRD_TRY(export_hidden(0));
         const double ln_bytes = 1.0 * T * Hd * 2 * 2;
         const double attn_flops = 4.0 * nb * c->bert_heads * S * 1.0 * S * 64;
         for (size_t i = 0; i < p->layers.size(); ++i) {
@@ -1008,6 +1021,7 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                 MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
                                            Hd, c->t_h, Hd, nullptr, 0, s, c->t_nrows));
             }
+            MRD_TRY(export_hidden(i + 1));
         }
         if (last_hidden) {
             // full last layer was computed: CLS rows (src/text_encoder.py:118) = first packed row of
@@ -1201,7 +1215,7 @@ int mrd_cnn_encoder_fwd(mrd_ctx* c, const void* images, int img_dtype, int B, in
 }
 
 int mrd_text_encoder_fwd(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype, int B,
-                         int S, float* cls, float* last_hidden, void* stream) {
+                         int S, float* cls, float* last_hidden, float* all_hidden, void* stream) {
     MRD_TRY(check_ctx(c));
     if (B <= 0) return 0;
     if (mask && (mask_dtype < MRD_DT_I64 || mask_dtype > MRD_DT_BF16)) {
@@ -1209,7 +1223,8 @@ int mrd_text_encoder_fwd(mrd_ctx* c, const long long* ids, const void* mask, int
         return -1;
     }
     MRD_TRY(ensure_batch_ws(c, B));
-    return run_bert(c, ids, mask, mask_dtype, B, S, cls, last_hidden, static_cast<cudaStream_t>(stream));
+    return run_bert(c, ids, mask, mask_dtype, B, S, cls, last_hidden, all_hidden,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int mrd_fusion_fwd(mrd_ctx* c, const float* img_emb, const float* txt_emb, int B, float* fused,
@@ -1282,7 +1297,7 @@ int mrd_multimodal_fwd(mrd_ctx* c, const void* images, int img_dtype, const long
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
     MRD_TRY(run_projection(c, bp, img_emb, s));
-    MRD_TRY(run_bert(c, ids, mask, mask_dtype, B, S, txt_emb, nullptr, s));
+    MRD_TRY(run_bert(c, ids, mask, mask_dtype, B, S, txt_emb, nullptr, nullptr, s));
     MRD_TRY(run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s));
     return run_head(c, bp, B, logits, probs, s);
 }

@@ -173,16 +173,21 @@ class Engine:
                                                         _stream(self.device)), "mrd_cnn_encoder_fwd")
         return emb, pooled, fmap
 
-    def text_encoder(self, input_ids, attention_mask, hidden: int = 768, want_hidden=False):
+    def text_encoder(self, input_ids, attention_mask, hidden: int = 768, want_hidden=False,
+                     all_layers: int = 0):
+        """all_layers = L > 0 additionally returns the [L+1,B,S,hidden] stack of hidden states."""
         ids, mask, code = self._text(input_ids, attention_mask)
         B, S = ids.shape
         cls = self._f32(B, hidden)
-        last = self._f32(B, S, hidden) if want_hidden else None
+        last = self._f32(B, S, hidden) if (want_hidden or all_layers) else None
+        stack = self._f32(all_layers + 1, B, S, hidden) if all_layers else None
         if B:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.mrd_text_encoder_fwd(self._ctx, ids.data_ptr(), _ptr(mask), code,
-                                                         B, S, cls.data_ptr(), _ptr(last),
+                                                         B, S, cls.data_ptr(), _ptr(last), _ptr(stack),
                                                          _stream(self.device)), "mrd_text_encoder_fwd")
+        if all_layers:
+            return cls, last, stack
         return cls, last
 
     def fusion(self, img_emb, txt_emb, hidden_dim: int, heads: int):

@@ -81,9 +81,15 @@ class TextEncoder(B200Module):
         cls, _ = self._engine().text_encoder(input_ids, attention_mask, self.embedding_dim)
         return cls
 
-    def get_all_hidden_states(self, input_ids, attention_mask):
-        raise NotImplementedError("per-layer hidden states are not exported by the B200 path yet "
-                                  "(SURVEY.md section 8(f).3)")
+    def get_all_hidden_states(self, input_ids, attention_mask) -> Tuple[torch.Tensor, tuple]:
+        """(last_hidden_state [B,S,768], hidden_states) with hidden_states a tuple of L+1 tensors
+        (embedding output, then every layer's output) - src/text_encoder.py:129-149.  Runs without
+        token packing so padded positions are computed as in the reference."""
+        self._check()
+        n_layers = len(self.encoder.encoder.layer)
+        _, last, stack = self._engine().text_encoder(input_ids, attention_mask, self.embedding_dim,
+                                                     all_layers=n_layers)
+        return last, tuple(stack.unbind(0))
 
     def get_last_hidden_state(self, input_ids, attention_mask) -> torch.Tensor:
         self._check()

@@ -270,3 +270,29 @@ def test_cls_tail_matches_full_last_layer(cuda, state):
     # attended positions of the full hidden state match the oracle too (padded rows are unspecified)
     for b, L in enumerate([48, 20, 1, 33, 48, 7]):
         assert _rel_rows(last[b, :L], ref[b, :L]) <= REL_TOL
+
+
+def test_all_hidden_states_vs_oracle(cuda, state):
+    """get_all_hidden_states (src/text_encoder.py:129-149): 13 tensors, each checked on the attended
+    positions against the oracle's per-layer states."""
+    import torch.nn.functional as F
+
+    model = _use(state, "sens")
+    lens = [40, 13, 27]
+    _, ids, mask = synth.make_inputs(3, 40, 77, lens, H=32, W=32)
+    with torch.no_grad():
+        last, states = model.text_encoder.get_all_hidden_states(ids.cuda(), mask.cuda())
+    assert len(states) == 13 and all(t.shape == (3, 40, 768) for t in states)
+    assert torch.equal(states[-1], last)
+    sd = {k: v.float() for k, v in state["sens"].items() if v.is_floating_point()}
+    with torch.no_grad():
+        ref_last = oracle.bert_encoder(sd, ids, mask)
+        e = "text_encoder.encoder.embeddings."
+        emb = F.layer_norm(sd[e + "word_embeddings.weight"][ids] + sd[e + "token_type_embeddings.weight"][0]
+                           + sd[e + "position_embeddings.weight"][:40], (768,), sd[e + "LayerNorm.weight"],
+                           sd[e + "LayerNorm.bias"], 1e-12)
+    for b, L in enumerate(lens):
+        assert _rel_rows(states[0][b, :L], emb[b, :L]) <= 5e-3      # embeddings: one bf16 rounding
+        assert _rel_rows(last[b, :L], ref_last[b, :L]) <= REL_TOL
+    # intermediate layers differ from their neighbours (really per-layer, not copies)
+    assert not torch.equal(states[5], states[6])
