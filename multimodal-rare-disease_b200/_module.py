@@ -47,11 +47,18 @@ class B200Module(nn.Module):
         eng.sync_weights(self._mrd_named())
         return eng
 
-    def configure_b200(self, img_chunk: int = 0, seq_chunk_tokens: int = 0) -> None:
-        """Micro-batch sizes of the engine (images per ResNet pass, tokens per BERT pass)."""
+    def configure_b200(self, img_chunk: int = 0, seq_chunk_tokens: int = 0, fp32_check=None) -> None:
+        """Micro-batch sizes of the engine (images per ResNet pass, tokens per BERT pass).
+
+        fp32_check=True switches this module's forwards to the library's plain-fp32 check kernels (no
+        bf16 anywhere, BatchNorm un-folded): a slow verification mode that matches the reference's own
+        fp32 forward to ~1e-5 (BASELINE.json north_star: 1e-4).  False switches back."""
         training, self.training = self.training, False
         try:
-            self._engine().configure(img_chunk, seq_chunk_tokens)
+            eng = self._engine()
+            eng.configure(img_chunk, seq_chunk_tokens)
+            if fp32_check is not None:
+                eng.set_option("fp32_check", 1.0 if fp32_check else 0.0)
         finally:
             self.training = training
 

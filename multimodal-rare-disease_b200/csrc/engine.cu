@@ -25,6 +25,7 @@
 
 #include "attention.h"
 #include "elementwise.h"
+#include "fp32_check.h"
 #include "gemm_conv.h"
 #include "tma_host.h"
 
@@ -134,6 +135,18 @@ struct mrd_ctx {
     int fusion_heads = 8;
     int fusion_residual = 1;
     int head_act = MRD_ACT_RELU;
+    // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
+    // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
+    bool fp32_check = false;
+    RawTable raw;
+    Fp32Arena f32_ws;
+    Fp32Opts f32_opts() const {
+        Fp32Opts o;
+        o.bert_heads = bert_heads; o.bert_ln_eps = bert_ln_eps; o.bn_eps = bn_eps;
+        o.fusion_ln_eps = fusion_ln_eps; o.fusion_heads = fusion_heads;
+        o.fusion_residual = fusion_residual; o.head_act = head_act;
+        return o;
+    }
 
     // ---- weights
     bool has_cnn = false, has_text = false, has_fusion = false, has_head = false;
@@ -1099,6 +1112,14 @@ int check_ctx(mrd_ctx* c) {
     return 0;
 }
 
+int fp32_images_only(int img_dtype) {
+    if (img_dtype != MRD_DT_F32) {
+        set_last_error("fp32 check mode takes fp32 images (dtype code %d given)", img_dtype);
+        return -1;
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ====================================================================== C ABI
@@ -1133,6 +1154,7 @@ int mrd_ctx_destroy(mrd_ctx* c) {
     if (c->cnn_ws.base) cudaFree(c->cnn_ws.base);
     if (c->text_ws.base) cudaFree(c->text_ws.base);
     if (c->batch_ws.base) cudaFree(c->batch_ws.base);
+    fp32_arena_free(&c->f32_ws);
     delete c;
     return 0;
 }
@@ -1158,6 +1180,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fusion_heads") c->fusion_heads = static_cast<int>(v);
     else if (k == "fusion_residual") { c->fusion_residual = v != 0.0; c->batch_plans.clear(); }
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
+    else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else {
         set_last_error("mrd_ctx_set_option: unknown option '%s'", k.c_str());
         return -1;
@@ -1178,6 +1201,10 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
         for (int j = 0; j < 4; ++j) x.d[j] = shapes[i * 4 + j];
         const std::string nm(names[i]);
         t.m.emplace(nm, x);
+        RawTensor rt;
+        rt.p = x.p;
+        for (int j = 0; j < 4; ++j) rt.d[j] = x.d[j];
+        c->raw[nm] = rt;
         any_cnn |= nm.rfind("cnn_encoder.", 0) == 0;
         any_text |= nm.rfind("text_encoder.", 0) == 0;
         any_fusion |= nm.rfind("fusion.", 0) == 0;
@@ -1207,6 +1234,12 @@ int mrd_cnn_encoder_fwd(mrd_ctx* c, const void* images, int img_dtype, int B, in
     MRD_TRY(check_ctx(c));
     if (B <= 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (c->fp32_check) {
+        MRD_TRY(fp32_images_only(img_dtype));
+        ++c->launches;
+        return fp32_cnn_encoder(c->raw, c->f32_opts(), &c->f32_ws, static_cast<const float*>(images), B, H,
+                                W, emb, feat_pooled, feat_map, s);
+    }
     MRD_TRY(ensure_batch_ws(c, B));
     MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, feat_pooled, feat_map, s));
     BatchPlan* bp;
@@ -1222,6 +1255,11 @@ int mrd_text_encoder_fwd(mrd_ctx* c, const long long* ids, const void* mask, int
         set_last_error("unknown mask dtype code %d", mask_dtype);
         return -1;
     }
+    if (c->fp32_check) {
+        ++c->launches;
+        return fp32_text_encoder(c->raw, c->f32_opts(), &c->f32_ws, ids, mask, mask_dtype, B, S, cls,
+                                 last_hidden, all_hidden, static_cast<cudaStream_t>(stream));
+    }
     MRD_TRY(ensure_batch_ws(c, B));
     return run_bert(c, ids, mask, mask_dtype, B, S, cls, last_hidden, all_hidden,
                     static_cast<cudaStream_t>(stream));
@@ -1236,6 +1274,10 @@ int mrd_fusion_fwd(mrd_ctx* c, const float* img_emb, const float* txt_emb, int B
         return -3;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (c->fp32_check) {
+        ++c->launches;
+        return fp32_fusion(c->raw, c->f32_opts(), &c->f32_ws, img_emb, txt_emb, B, fused, attn_i2t, attn_t2i, s);
+    }
     MRD_TRY(ensure_batch_ws(c, B));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
@@ -1260,6 +1302,10 @@ int mrd_head_fwd(mrd_ctx* c, const float* x, int B, float* logits, float* probs,
         return -3;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (c->fp32_check) {
+        ++c->launches;
+        return fp32_head(c->raw, c->f32_opts(), &c->f32_ws, x, B, logits, probs, s);
+    }
     MRD_TRY(ensure_batch_ws(c, B));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
@@ -1293,6 +1339,25 @@ int mrd_multimodal_fwd(mrd_ctx* c, const void* images, int img_dtype, const long
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MRD_TRY(ensure_batch_ws(c, B));
+    if (c->fp32_check) {
+        // every stage in plain fp32 on the raw parameters; embeddings nobody asked for live in scratch
+        MRD_TRY(fp32_images_only(img_dtype));
+        float* sc = c->b_scratch_f32;
+        float* ie = img_emb ? img_emb : sc;
+        float* te = txt_emb ? txt_emb : sc + 1LL * B * c->img_emb_dim;
+        float* fe = fused ? fused : sc + 1LL * B * (c->img_emb_dim + c->hidden);
+        if (c->img_emb_dim + c->hidden + c->fusion_dim > 2048) {
+            set_last_error("fp32 check: embedding widths exceed the scratch row");
+            return -1;
+        }
+        const Fp32Opts o = c->f32_opts();
+        c->launches += 4;
+        MRD_TRY(fp32_cnn_encoder(c->raw, o, &c->f32_ws, static_cast<const float*>(images), B, H, W, ie,
+                                 nullptr, nullptr, s));
+        MRD_TRY(fp32_text_encoder(c->raw, o, &c->f32_ws, ids, mask, mask_dtype, B, S, te, nullptr, nullptr, s));
+        MRD_TRY(fp32_fusion(c->raw, o, &c->f32_ws, ie, te, B, fe, attn_i2t, attn_t2i, s));
+        return fp32_head(c->raw, o, &c->f32_ws, fe, B, logits, probs, s);
+    }
     MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, nullptr, nullptr, s));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));

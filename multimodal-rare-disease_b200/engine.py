@@ -69,6 +69,11 @@ class Engine:
             _lib.check(self.lib.mrd_ctx_configure(self._ctx, int(img_chunk), int(seq_chunk_tokens)),
                        "mrd_ctx_configure")
 
+    def set_option(self, key: str, value: float) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrd_ctx_set_option(self._ctx, key.encode(), float(value)),
+                       f"mrd_ctx_set_option({key})")
+
     def profile(self, enable: bool) -> None:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mrd_ctx_profile(self._ctx, 1 if enable else 0), "mrd_ctx_profile")
@@ -125,6 +130,9 @@ class Engine:
             _lib.check(self.lib.mrd_ctx_load_weights(self._ctx, n, names, ptrs, shapes,
                                                      _stream(self.device)), "mrd_ctx_load_weights")
         self._sig = sig
+        # the fp32 check mode and the training step read the raw fp32 tensors handed over above: keep
+        # them (views of the parameters, or fp32 copies of non-fp32 ones) alive until the next hand-over
+        self._keep = keep
         return True
 
     # ------------------------------------------------------------------ input normalisation
