@@ -197,6 +197,56 @@ int mrd_attention_use_tcgen05(int on);
 /* attention_mask [B,S] -> additive key bias (0 / -inf). */
 int mrd_mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step: what autograd does around MultimodalClassifier.forward in the
+ * reference's trainers (src/train.py:247-321, src/train_multimodal.py:508-543).  The loss, gradient
+ * clipping and the optimizer stay with the caller, exactly as in the reference (criterion(logits,
+ * labels).backward(); clip_grad_norm_; optimizer.step()): the library provides the forward in train
+ * mode and the backward from d(loss)/d(logits) to every trainable parameter.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Train-mode forward (dropout active with the probabilities set through mrd_ctx_set_option:
+ * "train.p_bert_hidden" 0.1, "train.p_bert_attn" 0.1, "train.p_text_out" 0.1, "train.p_cnn_proj" 0.5,
+ * "train.p_fusion" 0.3, "train.p_head" 0.5, "train.pad_idx" 0; masks are a pure function of `seed`).
+ * Keeps the activations the backward needs inside the context; one forward may be pending at a time.
+ * The ResNet50 backbone must be frozen (the reference default, src/config.py:64) and is run forward
+ * only.  S <= 128, B <= one pass.  logits: f32 [B,C]. */
+int mrd_train_forward(mrd_ctx* ctx, const void* images, int img_dtype, const long long* ids,
+                      const void* mask, int mask_dtype, int B, int H, int W, int S,
+                      unsigned long long seed, float* logits, void* stream);
+
+/* Backward of the pending mrd_train_forward.  dlogits: f32 [B,C].  names/grads: state_dict names of the
+ * parameters that want a gradient and their f32 gradient buffers (same shapes as the parameters,
+ * ZEROED by the caller: gradients are accumulated into them); parameters that are absent or NULL are
+ * treated as frozen.  query_proj / key_proj of the length-1 cross attention receive exactly zero
+ * (softmax over one key, src/fusion_model.py:138-165), the BERT pooler is unused. */
+int mrd_train_backward(mrd_ctx* ctx, const float* dlogits, int n, const char* const* names,
+                       float* const* grads, void* stream);
+
+/* out[i] = 1 if element i of dropout site `site` is kept under (seed, p), else 0 (i < n).  The masks
+ * of mrd_train_forward are reproducible with this (tests; csrc/rng.cuh documents the site ids and the
+ * element indexing). */
+int mrd_dropout_mask(unsigned long long seed, unsigned int site, double p, long long n, float* out,
+                     void* stream);
+
+/* mrd_attention_bf16 with dropout on the probabilities (train mode); element index of (b,h,q,k) is
+ * ((b*heads + h)*S + q)*S + k.  S <= 128. */
+int mrd_attention_train_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads,
+                             unsigned long long seed, unsigned int site, double p, void* out,
+                             void* stream);
+
+/* Backward of the fused attention: qkv / dqkv bf16 [rows, 3*heads*64], ctx (forward output) / dctx bf16
+ * [rows, heads*64]; dQ is the gradient of the pre-scaled Q.  seq_off as mrd_attention_varlen_bf16 or
+ * NULL for the dense layout.  S <= 128 (one 128x128 tile per (sample, head)). */
+int mrd_attention_bwd_bf16(const void* qkv, const void* ctx, const void* dctx, const float* mask_bias,
+                           const int* seq_off, int B, int S, int heads, unsigned long long seed,
+                           unsigned int site, double p, void* dqkv, void* stream);
+
+/* Backward of y = LayerNorm(s)*gamma + beta on bf16 rows: dx (bf16), dgamma / dbeta accumulated into
+ * f32 buffers (either may be NULL).  width in {256,512,768,1024}. */
+int mrd_layernorm_bwd_bf16(const void* s_in, const void* dy, const float* gamma, float eps, int rows,
+                           int width, void* dx, float* dgamma, float* dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

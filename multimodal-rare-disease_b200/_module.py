@@ -32,13 +32,13 @@ class B200Module(nn.Module):
         except StopIteration:
             return torch.device("cpu")
 
-    def _engine(self) -> Engine:
+    def _engine(self, allow_training: bool = False) -> Engine:
         """The engine for the device the parameters live on, with up-to-date packed weights."""
-        if self.training:
+        if self.training and not allow_training:
             raise NotImplementedError(
-                "the B200 path implements the inference forward (eval mode) only; call .eval() first. "
-                "The training step (dropout, batch-statistics BatchNorm, backward) is scheduled next "
-                "(SURVEY.md section 8(f)) and deliberately has no silent PyTorch fallback.")
+                "this module's B200 path implements the inference forward (eval mode) only; call .eval() "
+                "first.  Train mode is implemented for MultimodalClassifier.forward (the training step of "
+                "SURVEY.md section 8(f)); there is deliberately no silent PyTorch fallback.")
         dev = self._mrd_device()
         eng = self.__dict__.get("_mrd_engine")
         if eng is None or eng.device != dev:

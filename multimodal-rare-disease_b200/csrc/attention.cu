@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "ptx.cuh"
+#include "rng.cuh"
 #include "tma_host.h"
 
 namespace mrd {
@@ -378,8 +379,12 @@ struct TcParams {
     const int* seq_off;    // packed layout or null
     __nv_bfloat16* out;
     int S_max, heads, items;
+    DropCfg drop;          // train mode: dropout on the probabilities (DROP instantiation only)
 };
 
+// DROP: the probabilities that feed P V are dropped / rescaled (attention_probs_dropout_prob in train
+// mode, HF:models/bert/modeling_bert.py:168-207); the softmax normaliser stays the undropped sum.
+template <bool DROP>
 __global__ void __launch_bounds__(kTcThreads, 4)
 attention_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t raw[];
@@ -489,6 +494,11 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int j = 0; j < 32; ++j) {
                     e[j] = fast_exp2(fmaf(__uint_as_float(v[j]) + bias_s[c0 + j], kLog2e, -ms));
                     sum += e[j];
+                    if (DROP) {
+                        const unsigned long long idx =
+                            (static_cast<unsigned long long>(item) * p.S_max + row) * p.S_max + (c0 + j);
+                        e[j] = drop_keep(p.drop, idx) ? e[j] * p.drop.scale : 0.0f;
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -547,11 +557,14 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
 }
 
 int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
-              int heads, long long rows_alloc, int blocked, __nv_bfloat16* out, cudaStream_t stream) {
+              int heads, long long rows_alloc, int blocked, __nv_bfloat16* out, cudaStream_t stream,
+              const DropCfg* drop) {
     constexpr int SMEM = 49152 + 1024 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) {
             set_last_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return -static_cast<int>(e);
@@ -559,6 +572,8 @@ int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_o
         attr_set = true;
     }
     TcParams p;
+    const bool dropping = drop != nullptr && drop->thresh != 0u;
+    p.drop = dropping ? *drop : DropCfg{0ull, 0u, 0u, 1.0f};
     // 3-D view {64 dims, rows, 3*heads column blocks}: token-major rows are 3*heads*64 elements apart
     // with the blocks side by side; in the blocked layout every block is a contiguous [rows,64] matrix
     const uint64_t nblk = static_cast<uint64_t>(3) * heads;
@@ -577,7 +592,10 @@ int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_o
     p.heads = heads;
     p.items = B * heads;
     const int grid = p.items < 148 * 4 ? p.items : 148 * 4;
-    attention_tc_kernel<<<grid, kTcThreads, SMEM, stream>>>(p);
+    if (dropping)
+        attention_tc_kernel<true><<<grid, kTcThreads, SMEM, stream>>>(p);
+    else
+        attention_tc_kernel<false><<<grid, kTcThreads, SMEM, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention_tc_kernel launch: %s", cudaGetErrorString(e));
@@ -594,8 +612,12 @@ bool attention_prefers_blocked_qkv(int S) { return S <= 128 && g_attention_tc; }
 
 int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
                       int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc,
-                      int blocked) {
+                      int blocked, const DropCfg* drop) {
     if (B <= 0 || S <= 0) return 0;
+    if (drop && drop->thresh != 0u && !(S <= 128 && g_attention_tc)) {
+        set_last_error("attention_forward: dropout on the probabilities is implemented on the tcgen05 path (S <= 128)");
+        return -1;
+    }
     if (blocked && !(S <= 128 && g_attention_tc)) {
         set_last_error("attention_forward: the blocked qkv layout is only read by the tcgen05 path (S <= 128)");
         return -1;
@@ -610,7 +632,7 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     // whole sequences fit one 128x128 tile: tcgen05 path (rows_alloc bounds the TMA view of qkv)
     if (S <= 128 && g_attention_tc && static_cast<long long>(B) * heads < 0x7fffffffLL)
         return launch_tc(qkv, mask_bias, seq_off, B, S, heads,
-                         rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream);
+                         rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream, drop);
     if (S > 64)
         return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
     return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);

@@ -27,7 +27,9 @@
 #include "elementwise.h"
 #include "fp32_check.h"
 #include "gemm_conv.h"
+#include "simt_gemm.h"
 #include "tma_host.h"
+#include "train_kernels.h"
 
 using namespace mrd;
 typedef __nv_bfloat16 bf16;
@@ -101,6 +103,10 @@ struct BatchPlan {
 
 }  // namespace
 
+namespace {
+struct TrainState;  // engine_train.cuh
+}
+
 struct ProfRecord {
     const char* label = "";
     int cat = 0;
@@ -137,6 +143,9 @@ struct mrd_ctx {
     int head_act = MRD_ACT_RELU;
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
+    TrainState* train = nullptr;   // training step state (engine_train.cuh), created on first use
+    long long text_ws_epoch = 0;   // bumped when the text workspace is re-carved (pointers change)
+    long long text_run_epoch = 0;  // bumped by every eval-mode BERT pass (overwrites the packing tables)
     bool fp32_check = false;
     RawTable raw;
     Fp32Arena f32_ws;
@@ -651,6 +660,7 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
 int ensure_text_ws(mrd_ctx* c, int tokens, int seqs) {
     if (c->text_ws.base && c->text_ws_tokens >= tokens && c->text_ws_seqs >= seqs) return 0;
     c->text_plans.clear();
+    ++c->text_ws_epoch;
     if (tokens < c->text_ws_tokens) tokens = c->text_ws_tokens;
     if (seqs < c->text_ws_seqs) seqs = c->text_ws_seqs;
     c->text_ws_seqs = seqs;
@@ -938,6 +948,7 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
         set_last_error("sequence length %d unsupported (1..%d)", S, c->max_pos < 512 ? c->max_pos : 512);
         return -1;
     }
+    ++c->text_run_epoch;
     int seqs = c->tok_chunk / S;
     if (seqs < 1) seqs = 1;
     if (seqs > B) seqs = B;
@@ -1112,6 +1123,8 @@ int check_ctx(mrd_ctx* c) {
     return 0;
 }
 
+#include "engine_train.cuh"
+
 int fp32_images_only(int img_dtype) {
     if (img_dtype != MRD_DT_F32) {
         set_last_error("fp32 check mode takes fp32 images (dtype code %d given)", img_dtype);
@@ -1155,6 +1168,7 @@ int mrd_ctx_destroy(mrd_ctx* c) {
     if (c->text_ws.base) cudaFree(c->text_ws.base);
     if (c->batch_ws.base) cudaFree(c->batch_ws.base);
     fp32_arena_free(&c->f32_ws);
+    train_free(c);
     delete c;
     return 0;
 }
@@ -1181,6 +1195,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fusion_residual") { c->fusion_residual = v != 0.0; c->batch_plans.clear(); }
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
+    else if (k.rfind("train.", 0) == 0) return train_set_option(c, k, v);
     else {
         set_last_error("mrd_ctx_set_option: unknown option '%s'", k.c_str());
         return -1;
@@ -1214,6 +1229,7 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cuda_fail(e, "mrd_ctx_load_weights: device sync");
     const size_t n_blocks = c->blocks.size(), n_layers = c->layers.size(), n_head = c->head_hidden.size();
+    if (c->train) train_invalidate_packs(c);
     if (any_cnn) MRD_TRY(load_cnn(c, t, s));
     if (any_text) MRD_TRY(load_text(c, t, s));
     if (any_fusion) MRD_TRY(load_fusion(c, t, s));
@@ -1411,6 +1427,58 @@ int mrd_ctx_profile_report(mrd_ctx* c, char* buf, int cap) {
         off += w;
     }
     return 0;
+}
+
+int mrd_train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
+                      int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
+                      void* stream) {
+    MRD_TRY(check_ctx(c));
+    if (B <= 0) return 0;
+    if (mask && (mask_dtype < MRD_DT_I64 || mask_dtype > MRD_DT_BF16)) {
+        set_last_error("unknown mask dtype code %d", mask_dtype);
+        return -1;
+    }
+    if (c->fp32_check) {
+        set_last_error("mrd_train_forward: the fp32 check mode covers the inference forward only");
+        return -1;
+    }
+    return train_forward(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int mrd_train_backward(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,
+                       void* stream) {
+    MRD_TRY(check_ctx(c));
+    GradTable gt;
+    gt.reserve(static_cast<size_t>(n) * 2);
+    for (int i = 0; i < n; ++i)
+        if (grads[i]) gt.emplace(names[i], grads[i]);
+    return train_backward(c, dlogits, gt, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_dropout_mask(unsigned long long seed, unsigned int site, double p, long long n, float* out, void* stream) {
+    return dropout_mask_f32(make_drop(seed, site, p), n, out, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_attention_bwd_bf16(const void* qkv, const void* ctx, const void* dctx, const float* mask_bias,
+                           const int* seq_off, int B, int S, int heads, unsigned long long seed,
+                           unsigned int site, double p, void* dqkv, void* stream) {
+    return attention_backward(static_cast<const bf16*>(qkv), static_cast<const bf16*>(ctx),
+                              static_cast<const bf16*>(dctx), mask_bias, seq_off, B, S, heads,
+                              make_drop(seed, site, p), static_cast<bf16*>(dqkv), static_cast<cudaStream_t>(stream));
+}
+
+int mrd_attention_train_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads,
+                             unsigned long long seed, unsigned int site, double p, void* out, void* stream) {
+    const DropCfg d = make_drop(seed, site, p);
+    return attention_forward(static_cast<const bf16*>(qkv), mask_bias, nullptr, B, S, heads,
+                             static_cast<bf16*>(out), static_cast<cudaStream_t>(stream), 0, 0, &d);
+}
+
+int mrd_layernorm_bwd_bf16(const void* s_in, const void* dy, const float* gamma, float eps, int rows, int width,
+                           void* dx, float* dgamma, float* dbeta, void* stream) {
+    return ln_bwd_bf16(static_cast<const bf16*>(s_in), static_cast<const bf16*>(dy), gamma, eps, rows, width,
+                       nullptr, static_cast<bf16*>(dx), dgamma, dbeta, static_cast<cudaStream_t>(stream));
 }
 
 long long mrd_ctx_launch_count(const mrd_ctx* c) { return c ? c->launches : 0; }

@@ -257,3 +257,48 @@ class Engine:
                     logits.data_ptr(), probs.data_ptr(), _ptr(img_e), _ptr(txt_e), _ptr(fused),
                     _ptr(a1), _ptr(a2), _stream(self.device)), "mrd_multimodal_fwd")
         return logits, probs, img_e, txt_e, fused, a1, a2
+
+    # ------------------------------------------------------------------ training step
+    def train_forward(self, images, input_ids, attention_mask, num_classes: int, seed: int) -> torch.Tensor:
+        """Train-mode forward (dropout active, activations kept inside the context) -> logits f32 [B,C]."""
+        images, icode = self._images(images)
+        ids, mask, mcode = self._text(input_ids, attention_mask)
+        B, _, H, W = images.shape
+        if ids.shape[0] != B:
+            raise ValueError(f"batch mismatch: {B} images vs {ids.shape[0]} token rows")
+        logits = self._f32(B, num_classes)
+        self._train_inputs = (images, ids, mask)   # the backward re-reads the ids
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_train_forward(
+                    self._ctx, images.data_ptr(), icode, ids.data_ptr(), _ptr(mask), mcode, B, H, W,
+                    ids.shape[1], C.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), logits.data_ptr(),
+                    _stream(self.device)), "mrd_train_forward")
+        return logits
+
+    def train_backward(self, dlogits: torch.Tensor, named_shapes) -> list:
+        """named_shapes: [(canonical state_dict name, shape)] of the parameters that want a gradient.
+        Returns their f32 gradients as views of ONE flat buffer (a single all-reduce bucket)."""
+        dl = dlogits.to(self.device, torch.float32).contiguous()
+        sizes = [int(torch.Size(sh).numel()) for _, sh in named_shapes]
+        offs, tot = [], 0
+        for n in sizes:
+            offs.append(tot)
+            tot += (n + 3) // 4 * 4      # keep every view 16-byte aligned
+        flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=self.device)
+        n = len(named_shapes)
+        names = (C.c_char_p * n)()
+        ptrs = (C.c_void_p * n)()
+        views = []
+        for i, ((name, sh), o, k) in enumerate(zip(named_shapes, offs, sizes)):
+            v = flat.narrow(0, o, k).view(sh)
+            views.append(v)
+            names[i] = name.encode()
+            ptrs[i] = v.data_ptr()
+        if dl.shape[0]:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_train_backward(self._ctx, dl.data_ptr(), n, names, ptrs,
+                                                       _stream(self.device)), "mrd_train_backward")
+        self._train_inputs = None
+        self.last_flat_grad = flat
+        return views

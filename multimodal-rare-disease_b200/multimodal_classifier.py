@@ -24,6 +24,23 @@ from .text_encoder import TextEncoder
 _ACT = {"relu": _lib.ACT_RELU, "gelu": _lib.ACT_GELU}
 
 
+class _TrainStep(torch.autograd.Function):
+    """autograd node of the train-mode forward: forward = mrd_train_forward, backward =
+    mrd_train_backward (one library call each).  Inputs after `nc` are the trainable parameters, so
+    `loss.backward()` fills their .grad exactly where the reference's autograd would
+    (src/train.py:307-320: backward -> clip_grad_norm_ -> optimizer.step stay the caller's)."""
+
+    @staticmethod
+    def forward(ctx, eng, images, input_ids, attention_mask, seed, named_shapes, nc, *params):
+        ctx.eng, ctx.named_shapes = eng, named_shapes
+        return eng.train_forward(images, input_ids, attention_mask, nc, seed)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
+        return (None,) * 7 + tuple(grads)
+
+
 class ClassificationHead(B200Module):
     """Linear/activation/dropout stack (src/multimodal_classifier.py:16-83)."""
 
@@ -107,6 +124,8 @@ class MultimodalClassifier(B200Module):
         """images [B,3,224,224], input_ids/attention_mask [B,S] -> {"logits","probs"} (+ embeddings
         and the fusion attention weights when return_embeddings=True), all fp32 on the model device."""
         self.text_encoder._check()
+        if self.training:
+            return self._forward_train(images, input_ids, attention_mask, return_embeddings)
         logits, probs, img_e, txt_e, fused, a1, a2 = self._engine().multimodal(
             images, input_ids, attention_mask, self._dims(), want_embeddings=return_embeddings,
             logits_out=logits_out)
@@ -117,6 +136,61 @@ class MultimodalClassifier(B200Module):
             out["fused_embedding"] = fused
             out["attention_info"] = {"image_to_text_attention": a1, "text_to_image_attention": a2}
         return out
+
+    # ---- training step ------------------------------------------------------------------------
+    def _train_options(self) -> Dict[str, float]:
+        mc = self.text_encoder.model_config
+        bn_train = any(m.training for m in self.cnn_encoder.backbone.modules()
+                       if isinstance(m, nn.modules.batchnorm._BatchNorm))
+        head_p = [m.p for m in self.classifier.classifier if isinstance(m, nn.Dropout)]
+        return {
+            "train.p_bert_hidden": float(getattr(mc, "hidden_dropout_prob", 0.0)),
+            "train.p_bert_attn": float(getattr(mc, "attention_probs_dropout_prob", 0.0)),
+            "train.p_text_out": float(self.text_encoder.dropout.p),
+            "train.p_cnn_proj": float(self.cnn_encoder.projection[2].p),
+            "train.p_fusion": float(self.fusion.fusion_layer.fusion[2].p),
+            "train.p_head": float(head_p[0]) if head_p else 0.0,
+            "train.pad_idx": float(getattr(mc, "pad_token_id", 0) or 0),
+            "train.bn_train": 1.0 if bn_train else 0.0,
+        }
+
+    def _trainable(self):
+        """[(canonical name, parameter)] the library differentiates; raises for what it cannot."""
+        out = []
+        for name, p in self._mrd_named():
+            if not isinstance(p, nn.Parameter) or not p.requires_grad:
+                continue
+            if name.startswith("cnn_encoder.backbone."):
+                raise NotImplementedError(
+                    f"{name} requires grad: the B200 training step keeps the ResNet50 backbone frozen "
+                    "(the reference default, src/config.py:64); backbone gradients are not implemented")
+            if ".pooler." in name:
+                continue   # unused with use_pooler_output=False: autograd leaves its .grad None as well
+            out.append((name, p))
+        return out
+
+    def _forward_train(self, images, input_ids, attention_mask, return_embeddings):
+        """Train-mode forward on the B200 path, differentiable through torch.autograd: the reference's
+        training loops (src/train.py:247-333, src/train_multimodal.py:508-556) run unchanged."""
+        if return_embeddings:
+            raise NotImplementedError("return_embeddings=True is an inference-path feature (eval mode)")
+        p_att = {self.fusion.fusion_layer.image_to_text_attention.dropout.p,
+                 self.fusion.fusion_layer.text_to_image_attention.dropout.p,
+                 self.fusion.fusion_layer.fusion[2].p}
+        if len(p_att) != 1:
+            raise NotImplementedError("the fusion dropouts must share one probability (FusionConfig.dropout)")
+        eng = self._engine(allow_training=True)
+        opts = self._train_options()
+        if self.__dict__.get("_mrd_train_opts") != opts:
+            for k, v in opts.items():
+                eng.set_option(k, v)
+            self.__dict__["_mrd_train_opts"] = opts
+        named = self._trainable()
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
+        shapes = tuple((n, tuple(p.shape)) for n, p in named)
+        logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes, self.num_classes,
+                                  *[p for _, p in named])
+        return {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
 
     def predict(self, images, input_ids, attention_mask) -> Tuple[torch.Tensor, torch.Tensor]:
         self.eval()

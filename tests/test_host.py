@@ -67,12 +67,19 @@ def test_no_cpu_fallback(model):
         model.classifier(torch.zeros(1, 512))
 
 
-def test_training_mode_is_refused_loudly(model):
+def test_training_mode_never_falls_back(model):
+    """Train mode: MultimodalClassifier.forward is the library's training step (CUDA only - on a CPU model it
+    fails like every other forward); the standalone sub-modules have no train-mode path and say so."""
     model.train()
     try:
-        with pytest.raises(NotImplementedError, match="eval"):
+        with pytest.raises(mrd_b200.MrdError, match="CUDA"):
             model(torch.zeros(1, 3, 224, 224), torch.zeros(1, 8, dtype=torch.long),
                   torch.ones(1, 8, dtype=torch.long))
+        with pytest.raises(NotImplementedError, match="eval"):
+            model.cnn_encoder(torch.zeros(1, 3, 224, 224))
+        with pytest.raises(NotImplementedError, match="inference-path"):
+            model(torch.zeros(1, 3, 224, 224), torch.zeros(1, 8, dtype=torch.long),
+                  torch.ones(1, 8, dtype=torch.long), return_embeddings=True)
     finally:
         model.eval()
 

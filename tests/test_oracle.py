@@ -89,4 +89,6 @@ def test_every_fixture_is_covered():
     names = {os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLD, "*.pt"))} - {"meta"}
     assert names == {"cfg1_plain_b4_s128", "cfg1_sens_b4_s128", "padded_sens_b5_s128",
                      "padded_sens_b3_s48", "text_sens_b2_s512", "text_plain_b3_s200",
-                     "image_sens_b2_160x96"}
+                     "image_sens_b2_160x96",
+                     # training-step fixtures: covered by tests/test_train_oracle.py
+                     "train_p0_bn_eval_b4_s32", "train_p0_bn_train_b4_s32"}

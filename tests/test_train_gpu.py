@@ -1,0 +1,339 @@
+"""Training step on the B200 path (BASELINE.json configs[4]) against the reference.
+
+Comparators: tests/golden/train_*.pt (one src/train.py-style step of the UNMODIFIED reference with
+dropout p = 0: loss, gradients, post-AdamW parameters) and oracle/train_oracle.py (pinned to the same
+fixtures by tests/test_train_oracle.py) for the runs with dropout, whose masks are exported from the
+library (mrd_dropout_mask) and fed to the oracle.
+Tolerances (bf16 activations and activation gradients, fp32 accumulation and fp32 parameter gradients;
+SURVEY.md 8(c)(5)): loss within 2e-2 relative; every parameter gradient within 5e-2 relative L2 of the
+reference's (sampled elements), total gradient norm within 2e-2; parameter delta of the AdamW step
+within 5e-2 relative L2 per group.
+"""
+
+import ctypes as C
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import synth
+from oracle import train_oracle as T
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+GRAD_TOL = 5e-2
+
+
+def _sample(t, stride):
+    return t.detach().float().flatten()[::stride].cpu()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _zero_dropout(model):
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    mc = model.text_encoder.model_config
+    mc.hidden_dropout_prob = 0.0
+    mc.attention_probs_dropout_prob = 0.0
+
+
+# --------------------------------------------------------------------------------------- kernels
+def _attention_ref(qkv, bias, B, S, heads, dctx, mask=None, p=0.0):
+    """fp32 autograd reference on the bf16-rounded inputs.  qkv [B*S, 3*heads*64] (Q pre-scaled)."""
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = x.view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias.view(B, 1, 1, S)
+    pr = torch.softmax(s, dim=-1)
+    if mask is not None:
+        pr = pr * mask.view(B, heads, S, S) / (1.0 - p)
+    o = (pr @ v).permute(0, 2, 1, 3).reshape(B * S, heads * 64)
+    o.backward(dctx.float())
+    return o.detach(), x.grad
+
+
+@pytest.mark.parametrize("B,S,lens,p", [(3, 128, [128, 77, 5], 0.0), (4, 48, [48, 48, 17, 1], 0.0),
+                                        (2, 128, [128, 100], 0.1), (5, 32, [32, 9, 32, 20, 31], 0.25)])
+def test_attention_backward_vs_autograd(cuda, lib, B, S, lens, p):
+    heads = 12
+    g = torch.Generator().manual_seed(5)
+    qkv = (torch.randn(B * S, 3 * heads * 64, generator=g) * 0.7).to(cuda, torch.bfloat16)
+    dctx = torch.randn(B * S, heads * 64, generator=g).to(cuda, torch.bfloat16)
+    bias = torch.zeros(B, S)
+    for b, L in enumerate(lens):
+        bias[b, L:] = float("-inf")
+    bias = bias.to(cuda)
+    seed, site = 1234567, 7
+    mask = None
+    if p > 0:
+        mask = torch.empty(B * heads * S * S, device=cuda)
+        assert lib.mrd_dropout_mask(C.c_ulonglong(seed), site, p, mask.numel(), _p(mask), _stream()) == 0
+        assert abs(mask.mean().item() - (1 - p)) < 0.01
+    # forward with the same mask (tcgen05 kernel), then the backward kernel
+    out = torch.empty(B * S, heads * 64, device=cuda, dtype=torch.bfloat16)
+    assert lib.mrd_attention_train_bf16(_p(qkv), _p(bias), B, S, heads, C.c_ulonglong(seed), site, p, _p(out),
+                                        _stream()) == 0, lib.mrd_last_error()
+    o_ref, d_ref = _attention_ref(qkv, bias, B, S, heads, dctx, mask, p)
+    live = (bias > float("-inf")).view(B * S)
+    err_o = (out.float()[live] - o_ref[live]).norm() / o_ref[live].norm()
+    assert err_o.item() <= 1e-2, err_o.item()
+    dqkv = torch.zeros_like(qkv)
+    assert lib.mrd_attention_bwd_bf16(_p(qkv), _p(out), _p(dctx), _p(bias), None, B, S, heads, C.c_ulonglong(seed),
+                                      site, p, _p(dqkv), _stream()) == 0, lib.mrd_last_error()
+    torch.cuda.synchronize()
+    # padded QUERY rows are outputs nobody reads: the engine never feeds them a gradient; here they do get
+    # one, so compare everything (keys beyond the length receive exactly zero dK/dV in both)
+    for name, sl in (("dQ", slice(0, 768)), ("dK", slice(768, 1536)), ("dV", slice(1536, 2304))):
+        a, r = dqkv.float()[:, sl], d_ref[:, sl]
+        err = ((a - r).norm() / r.norm()).item()
+        assert err <= 2e-2, (name, err)
+
+
+def test_attention_backward_packed_layout(cuda, lib):
+    """Token-packed rows (seq_off) give the same gradients as the dense layout with a key bias."""
+    B, S, heads, lens = 4, 64, 12, [64, 30, 1, 47]
+    g = torch.Generator().manual_seed(6)
+    qkv = (torch.randn(B * S, 2304, generator=g) * 0.7).to(cuda, torch.bfloat16)
+    dctx = torch.randn(B * S, 768, generator=g).to(cuda, torch.bfloat16)
+    ctx = torch.randn(B * S, 768, generator=g).to(cuda, torch.bfloat16)
+    rows = torch.cat([torch.arange(L) + b * S for b, L in enumerate(lens)]).to(cuda)
+    off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda)
+    bias = torch.zeros(B, S)
+    for b, L in enumerate(lens):
+        bias[b, L:] = float("-inf")
+    bias = bias.to(cuda)
+    dctx[(bias == float("-inf")).view(B * S).cpu()] = 0   # padded queries do not exist in the packed layout
+    d_dense = torch.zeros_like(qkv)
+    assert lib.mrd_attention_bwd_bf16(_p(qkv), _p(ctx), _p(dctx), _p(bias), None, B, S, heads, C.c_ulonglong(1), 0,
+                                      0.0, _p(d_dense), _stream()) == 0
+    pq, pc, pd = qkv[rows].contiguous(), ctx[rows].contiguous(), dctx[rows].contiguous()
+    d_pack = torch.zeros_like(pq)
+    assert lib.mrd_attention_bwd_bf16(_p(pq), _p(pc), _p(pd), None, _p(off), B, S, heads, C.c_ulonglong(1), 0, 0.0,
+                                      _p(d_pack), _stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(d_pack, d_dense[rows])
+
+
+@pytest.mark.parametrize("width", [768, 512])
+def test_layernorm_backward_vs_autograd(cuda, lib, width):
+    rows = 1000
+    g = torch.Generator().manual_seed(8)
+    s_in = (torch.randn(rows, width, generator=g) * 2 + 0.3).to(cuda, torch.bfloat16)
+    dy = torch.randn(rows, width, generator=g).to(cuda, torch.bfloat16)
+    gamma = (0.5 + torch.rand(width, generator=g)).to(cuda)
+    x = s_in.float().requires_grad_(True)
+    gm = gamma.clone().requires_grad_(True)
+    bt = torch.zeros(width, device=cuda, requires_grad=True)
+    F.layer_norm(x, (width,), gm, bt, 1e-12).backward(dy.float())
+    dx = torch.empty_like(s_in)
+    dg, db = torch.zeros(width, device=cuda), torch.zeros(width, device=cuda)
+    assert lib.mrd_layernorm_bwd_bf16(_p(s_in), _p(dy), _p(gamma), 1e-12, rows, width, _p(dx), _p(dg), _p(db),
+                                      _stream()) == 0, lib.mrd_last_error()
+    torch.cuda.synchronize()
+    assert ((dx.float() - x.grad).norm() / x.grad.norm()).item() <= 1e-2
+    assert ((dg - gm.grad).norm() / gm.grad.norm()).item() <= 1e-4
+    assert ((db - bt.grad).norm() / bt.grad.norm()).item() <= 1e-4
+
+
+def test_dropout_mask_statistics(cuda, lib):
+    n = 1 << 20
+    m = torch.empty(n, device=cuda)
+    for p in (0.1, 0.3, 0.5):
+        assert lib.mrd_dropout_mask(C.c_ulonglong(99), 3, p, n, _p(m), _stream()) == 0
+        assert abs(m.mean().item() - (1 - p)) < 3e-3
+        m2 = torch.empty(n, device=cuda)
+        assert lib.mrd_dropout_mask(C.c_ulonglong(99), 4, p, n, _p(m2), _stream()) == 0
+        # different sites are independent: agreement rate = (1-p)^2 + p^2
+        assert abs((m == m2).float().mean().item() - ((1 - p) ** 2 + p ** 2)) < 5e-3
+    assert lib.mrd_dropout_mask(C.c_ulonglong(99), 3, 0.0, n, _p(m), _stream()) == 0
+    assert bool((m == 1).all())
+
+
+# --------------------------------------------------------------------------------------- full step
+@pytest.fixture(scope="module")
+def sens():
+    return synth.sensitise(synth.build_model(0).state_dict(), 1)
+
+
+def _train_model(sens, zero_dropout=True):
+    model = synth.build_model(0)
+    model.load_state_dict(sens)
+    if zero_dropout:
+        _zero_dropout(model)
+    model = model.to("cuda:0")
+    model.train()
+    model.cnn_encoder.backbone.eval()   # frozen backbone on running statistics
+    return model
+
+
+def test_train_step_vs_reference_fixture(cuda, sens):
+    """One src/train.py-style step through the module API: loss.backward() fills .grad through the library's
+    backward; clip_grad_norm_ and torch.optim.AdamW stay the caller's, as in the reference."""
+    fix = torch.load(os.path.join(GOLD, "train_p0_bn_eval_b4_s32.pt"))
+    model = _train_model(sens)
+    images, ids, mask = synth.make_inputs(fix["B"], fix["S"], fix["seed"], fix["lengths"], H=fix["H"], W=fix["W"])
+    labels = torch.tensor(fix["labels"]).cuda()
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    opt = torch.optim.AdamW(model.parameters(), lr=fix["lr"], weight_decay=fix["weight_decay"])
+    opt.zero_grad()
+    out = model(images.cuda(), ids.cuda(), mask.cuda())
+    assert out["logits"].requires_grad and out["probs"].shape == (fix["B"], 10)
+    loss = nn.CrossEntropyLoss()(out["logits"], labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - fix["loss"]) <= 2e-2 * abs(fix["loss"]), (loss.item(), fix["loss"])
+    named = dict(model.named_parameters())
+    got = {k for k, p in named.items() if p.grad is not None}
+    assert got == set(fix["grads"]), (sorted(got ^ set(fix["grads"]))[:5])
+    report = []
+    for k, ref in fix["grads"].items():
+        g = named[k].grad
+        assert g.dtype == torch.float32 and g.shape == named[k].shape
+        if ref["norm"] == 0.0:
+            assert g.abs().max().item() == 0.0, k
+            continue
+        if ref["norm"] < 1e-5:   # key biases (softmax shift invariance): noise in both implementations
+            assert g.norm().item() <= 1e-2 * fix["total_norm"], k
+            continue
+        err = (_sample(g, ref["stride"]) - ref["sample"]).norm().item() / ref["sample"].norm().item()
+        report.append((err, k, g.norm().item() / ref["norm"]))
+    report.sort(reverse=True)
+    print("worst gradients (rel err, name, norm ratio):", report[:6])
+    for err, k, ratio in report:
+        assert err <= GRAD_TOL, (k, err, ratio)
+    total = nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    assert abs(total.item() - fix["total_norm"]) <= 2e-2 * fix["total_norm"]
+    opt.step()
+    torch.cuda.synchronize()
+    # parameter deltas of the AdamW step, relative L2 per parameter group
+    groups = {}
+    for k, ref in fix["post"].items():
+        if fix["grads"][k]["norm"] < 1e-5:
+            continue
+        pre = _sample(before[k], ref["stride"])
+        d_ref, d_got = ref["sample"] - pre, _sample(named[k], ref["stride"]) - pre
+        a = groups.setdefault(k.split(".")[0], [0.0, 0.0])
+        a[0] += (d_got - d_ref).norm().item() ** 2
+        a[1] += d_ref.norm().item() ** 2
+    rel = {k: (v[0] / v[1]) ** 0.5 for k, v in groups.items()}
+    print("AdamW delta rel-L2 per group:", rel)
+    for k, v in rel.items():
+        assert v <= 5e-2, (k, v)
+    # the next forward sees the updated parameters (packed weights are refreshed)
+    out2 = model(images.cuda(), ids.cuda(), mask.cuda())
+    assert not torch.equal(out2["logits"], out["logits"])
+
+
+def _export_masks(lib, model, seed, B, S, opts):
+    """The masks mrd_train_forward drew for `seed`, in the layout oracle.train_oracle expects
+    (csrc/rng.cuh / engine_train.cuh: site ids and element indexing; all-ones attention mask, so packed row
+    r = b*S + j)."""
+    dev = torch.device("cuda:0")
+
+    def mk(site, p, shape):
+        n = 1
+        for d in shape:
+            n *= d
+        m = torch.empty(n, device=dev)
+        assert lib.mrd_dropout_mask(C.c_ulonglong(seed), site, p, n, _p(m), _stream()) == 0
+        return (m.view(shape) / (1.0 - p)).cpu() if p > 0 else None
+
+    ph, pa = opts["train.p_bert_hidden"], opts["train.p_bert_attn"]
+    masks = {"emb": mk(1000, ph, (B, S, 768)), "text_out": mk(1001, opts["train.p_text_out"], (B, 768)),
+             "cnn_proj": mk(1002, opts["train.p_cnn_proj"], (B, 512)),
+             "i2t": mk(1003, opts["train.p_fusion"], (B, 8)), "t2i": mk(1004, opts["train.p_fusion"], (B, 8)),
+             "fusion_mlp": mk(1005, opts["train.p_fusion"], (B, 512)),
+             "head.0": mk(1010, opts["train.p_head"], (B, 256)), "head.1": mk(1011, opts["train.p_head"], (B, 128))}
+    for l in range(12):
+        masks[f"attn.{l}"] = mk(16 * l, pa, (B, 12, S, S))
+        masks[f"attn_out.{l}"] = mk(16 * l + 1, ph, (B, S, 768))
+        masks[f"ffn_out.{l}"] = mk(16 * l + 2, ph, (B, S, 768))
+    return {k: v for k, v in masks.items() if v is not None}
+
+
+def test_train_step_with_dropout_vs_oracle(cuda, lib, sens):
+    """Dropout active at the reference's default probabilities; the oracle receives the library's own masks."""
+    B, S = 3, 32
+    model = _train_model(sens, zero_dropout=False)
+    images, ids, mask = synth.make_inputs(B, S, 51, None, H=64, W=64)
+    labels = torch.tensor([2, 9, 4])
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    torch.manual_seed(77)
+    out = model(images.cuda(), ids.cuda(), mask.cuda())
+    loss = F.cross_entropy(out["logits"], labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    masks = _export_masks(lib, model, seed, B, S, model._train_options())
+    assert len(masks) == 8 + 36
+    ref_loss, ref_logits, ref_grads = T.loss_and_grads(sens, images, ids, mask, labels, masks=masks)
+    assert abs(loss.item() - ref_loss.item()) <= 3e-2 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    named = dict(model.named_parameters())
+    report = []
+    tot = torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values())).item()
+    for k, r in ref_grads.items():
+        g = named[k].grad.float().cpu()
+        if r.norm().item() < 1e-5 * tot:
+            assert g.norm().item() <= 1e-2 * tot, k
+            continue
+        report.append((((g - r).norm() / r.norm()).item(), k))
+    report.sort(reverse=True)
+    print("dropout step, worst gradients:", report[:6])
+    for err, k in report:
+        assert err <= GRAD_TOL, (k, err)
+    # a different seed gives different masks, hence different logits
+    out2 = model(images.cuda(), ids.cuda(), mask.cuda())
+    assert not torch.equal(out2["logits"], out["logits"])
+
+
+def test_training_loop_reduces_loss(cuda):
+    """A few steps of the reference's loop shape on a fixed batch: the loss must fall (plain random-init
+    weights, padded sequences, dropout on)."""
+    torch.manual_seed(3)
+    model = synth.build_model(0).to("cuda:0")
+    model.train()
+    model.cnn_encoder.backbone.eval()
+    images, ids, mask = synth.make_inputs(8, 48, 61, [48, 30, 12, 48, 7, 25, 40, 3], H=64, W=64)
+    labels = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7]).cuda()
+    images, ids, mask = images.cuda(), ids.cuda(), mask.cuda()
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=0.05)
+    crit = nn.CrossEntropyLoss()
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = crit(model(images, ids, mask)["logits"], labels)
+        loss.backward()
+        nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        losses.append(loss.item())
+    print("losses", [round(x, 3) for x in losses])
+    assert all(x == x for x in losses)
+    assert sum(losses[-3:]) / 3 < sum(losses[:3]) / 3 - 0.05
+    # eval mode afterwards uses the updated weights on the inference path
+    model.eval()
+    with torch.no_grad():
+        pred = model(images, ids, mask)["logits"]
+    assert torch.isfinite(pred).all()
+
+
+def test_train_mode_refuses_what_it_cannot_do(cuda):
+    model = synth.build_model(0).to("cuda:0")
+    model.train()          # BatchNorm in train mode: batch statistics are not on this path yet
+    images, ids, mask = synth.make_inputs(2, 16, 1, None, H=32, W=32)
+    with pytest.raises(Exception, match="BatchNorm|backbone"):
+        model(images.cuda(), ids.cuda(), mask.cuda())
+    model.cnn_encoder.backbone.eval()
+    model.cnn_encoder.backbone.layer4.requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="backbone"):
+        model(images.cuda(), ids.cuda(), mask.cuda())
