@@ -64,6 +64,14 @@ def sensitise(sd: Dict[str, torch.Tensor], seed: int = 1) -> Dict[str, torch.Ten
     return out
 
 
+def train_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Weights of the training-step fixtures (oracle/make_golden_train.py): plain random init with the
+    sensitised LayerNorm parameters."""
+    plain = build_model(seed).state_dict()
+    full = sensitise(plain, 1)
+    return {k: (full[k] if ("LayerNorm" in k or "layer_norm" in k) else v.clone()) for k, v in plain.items()}
+
+
 def checksum(sd: Dict[str, torch.Tensor]) -> str:
     """Order-independent digest of a state_dict's float tensors (bit-exact)."""
     h = hashlib.sha256()

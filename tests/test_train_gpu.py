@@ -163,7 +163,9 @@ def test_dropout_mask_statistics(cuda, lib):
 # --------------------------------------------------------------------------------------- full step
 @pytest.fixture(scope="module")
 def sens():
-    return synth.sensitise(synth.build_model(0).state_dict(), 1)
+    """Weights of the training fixtures: plain random init + sensitised LayerNorm parameters (small logits, so
+    softmax - onehot is well conditioned; see oracle/make_golden_train.py)."""
+    return synth.train_weights(0)
 
 
 def _train_model(sens, zero_dropout=True):
@@ -205,6 +207,9 @@ def test_train_step_vs_reference_fixture(cuda, sens):
             continue
         if ref["norm"] < 1e-5:   # key biases (softmax shift invariance): noise in both implementations
             assert g.norm().item() <= 1e-2 * fix["total_norm"], k
+            continue
+        if ref["sample"].norm().item() < 1e-3 * ref["norm"]:   # sparse gradient (word embeddings): norm only
+            assert abs(g.norm().item() - ref["norm"]) <= GRAD_TOL * ref["norm"], k
             continue
         err = (_sample(g, ref["stride"]) - ref["sample"]).norm().item() / ref["sample"].norm().item()
         report.append((err, k, g.norm().item() / ref["norm"]))
@@ -297,20 +302,56 @@ def test_train_step_with_dropout_vs_oracle(cuda, lib, sens):
     assert not torch.equal(out2["logits"], out["logits"])
 
 
+def test_backward_only_linear_loss_sensitised(cuda):
+    """Backward in isolation on the sensitised weights (|logits| ~ 14): a loss that is LINEAR in the logits
+    makes d(loss)/d(logits) identical for both implementations, so the gradient error measured here is the
+    backward pass's own (plus the forward activations it reuses), not the softmax's conditioning."""
+    sd = synth.sensitise(synth.build_model(0).state_dict(), 1)
+    model = _train_model(sd)
+    B, S = 5, 64
+    images, ids, mask = synth.make_inputs(B, S, 71, [64, 33, 64, 2, 17], H=96, W=64)
+    R = torch.randn(B, 10, generator=torch.Generator().manual_seed(9))
+    out = model(images.cuda(), ids.cuda(), mask.cuda())
+    (out["logits"] * R.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    names = T.trainable_names(sd)
+    work = {k: (v.detach().clone().float().requires_grad_(k in set(names)) if v.is_floating_point() else v)
+            for k, v in sd.items()}
+    (T.train_forward(work, images, ids, mask) * R).sum().backward()
+    named = dict(model.named_parameters())
+    tot = torch.sqrt(sum((work[k].grad.double() ** 2).sum() for k in names if work[k].grad is not None)).item()
+    report = []
+    for k in names:
+        r = work[k].grad if work[k].grad is not None else torch.zeros_like(work[k])
+        g = named[k].grad.float().cpu()
+        if r.norm().item() < 1e-5 * tot:
+            assert g.norm().item() <= 1e-2 * tot, k
+            continue
+        report.append((((g - r).norm() / r.norm()).item(), k))
+    report.sort(reverse=True)
+    print("linear loss, worst gradients:", report[:6])
+    for err, k in report:
+        assert err <= GRAD_TOL, (k, err)
+
+
 def test_training_loop_reduces_loss(cuda):
     """A few steps of the reference's loop shape on a fixed batch: the loss must fall (plain random-init
-    weights, padded sequences, dropout on)."""
+    weights, padded sequences, dropout on at a reduced rate so 20 steps are decisive)."""
     torch.manual_seed(3)
-    model = synth.build_model(0).to("cuda:0")
+    model = synth.build_model(0)
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = min(m.p, 0.1)
+    model = model.to("cuda:0")
     model.train()
     model.cnn_encoder.backbone.eval()
     images, ids, mask = synth.make_inputs(8, 48, 61, [48, 30, 12, 48, 7, 25, 40, 3], H=64, W=64)
     labels = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7]).cuda()
     images, ids, mask = images.cuda(), ids.cuda(), mask.cuda()
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=0.05)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
     crit = nn.CrossEntropyLoss()
     losses = []
-    for _ in range(12):
+    for _ in range(20):
         opt.zero_grad()
         loss = crit(model(images, ids, mask)["logits"], labels)
         loss.backward()
@@ -319,7 +360,7 @@ def test_training_loop_reduces_loss(cuda):
         losses.append(loss.item())
     print("losses", [round(x, 3) for x in losses])
     assert all(x == x for x in losses)
-    assert sum(losses[-3:]) / 3 < sum(losses[:3]) / 3 - 0.05
+    assert sum(losses[-3:]) / 3 < sum(losses[:3]) / 3 - 0.5
     # eval mode afterwards uses the updated weights on the inference path
     model.eval()
     with torch.no_grad():

@@ -19,7 +19,7 @@ def _sample(t, stride):
 
 @pytest.fixture(scope="module")
 def sens():
-    return synth.sensitise(synth.build_model(0).state_dict(), 1)
+    return synth.train_weights(0)
 
 
 @pytest.mark.parametrize("name", ["train_p0_bn_eval_b4_s32", "train_p0_bn_train_b4_s32"])
