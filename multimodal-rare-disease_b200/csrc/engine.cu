@@ -145,6 +145,7 @@ struct mrd_ctx {
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
     TrainState* train = nullptr;   // training step state (engine_train.cuh), created on first use
     long long text_ws_epoch = 0;   // bumped when the text workspace is re-carved (pointers change)
+    long long cnn_ws_epoch = 0;    // same for the ResNet workspace
     long long text_run_epoch = 0;  // bumped by every eval-mode BERT pass (overwrites the packing tables)
     bool fp32_check = false;
     RawTable raw;
@@ -547,6 +548,7 @@ int ensure_cnn_ws(mrd_ctx* c, int H, int W) {
     if (c->cnn_ws.base && c->cnn_ws_B == Bc && c->cnn_ws_H == H && c->cnn_ws_W == W) return 0;
     c->cnn_plans.clear();
     c->pads.clear();
+    ++c->cnn_ws_epoch;
     {
         int h = H / 4, w = W / 4;
         for (const Bottleneck& b : c->blocks) {

@@ -37,8 +37,11 @@ struct TrainLayerPlan {
     GemmLaunch d_g0, d_ctx0;              // the same with A = d_s (no dropout mask between LayerNorm and dense)
 };
 
+struct TrainCnn;
+
 struct TrainState {
     TrainOpts o;
+    TrainCnn* cnn = nullptr;              // batch-statistics backbone (created when bn_train is first used)
     std::vector<TrainLayerWt> wt;
     bool packs_valid = false;
     // plan / workspace for one (B, S)
@@ -77,13 +80,19 @@ TrainState* train_state(mrd_ctx* c) {
     return c->train;
 }
 
+void train_cnn_invalidate(TrainState* t);
+void train_cnn_free(TrainState* t);
+
 void train_invalidate_packs(mrd_ctx* c) {
-    if (c->train) c->train->packs_valid = false;
+    if (!c->train) return;
+    c->train->packs_valid = false;
+    train_cnn_invalidate(c->train);
 }
 
 void train_free(mrd_ctx* c) {
     if (!c->train) return;
     if (c->train->ws.base) cudaFree(c->train->ws.base);
+    train_cnn_free(c->train);
     delete c->train;
     c->train = nullptr;
 }
@@ -249,6 +258,226 @@ int train_ensure_plan(mrd_ctx* c, int B, int S) {
     return 0;
 }
 
+// ---- frozen backbone under model.train(): BatchNorm on batch statistics --------------------------------
+// The reference's default training configuration freezes the backbone's parameters but leaves its
+// BatchNorm layers in train mode (src/cnn_encoder.py:102-106 only clears requires_grad), so every
+// convolution is followed by batch statistics, normalisation and a running-stat update
+// (TV:models/resnet.py:143-163 under nn.Module.train()).  Convolutions run on the same tcgen05 implicit-GEMM
+// kernel with un-folded weights; statistics / normalise+residual+ReLU are two HBM-bound passes.
+struct TrainCnn {
+    bool packed = false;
+    bf16* stem_w = nullptr;
+    float *ones = nullptr, *zeros = nullptr;     // [2048] identity BatchNorm for the packers / zero bias
+    std::vector<Bottleneck> blocks;              // raw (un-folded) filters
+    float* stats = nullptr;                      // [sites][4][2048]: sum, sumsq, scale, shift
+    std::vector<std::string> bn_names;           // site -> "cnn_encoder.backbone....bnX"
+    int B = 0, H = 0, W = 0;
+    long long ws_epoch = -1;
+    CnnPlan plan;
+};
+
+TrainCnn* train_cnn(mrd_ctx* c) {
+    TrainState* t = train_state(c);
+    if (!t->cnn) t->cnn = new TrainCnn();
+    return t->cnn;
+}
+
+int train_cnn_pack(mrd_ctx* c, cudaStream_t s) {
+    TrainCnn* tc = train_cnn(c);
+    if (tc->packed) return 0;
+    const std::string bb = "cnn_encoder.backbone.";
+    if (!tc->ones) {
+        MRD_TRY(walloc(c, &tc->ones, 2048));
+        MRD_TRY(walloc(c, &tc->zeros, 2048));
+        MRD_TRY(fill_f32(tc->ones, 2048, 1.0f, s));
+        MRD_TRY(fill_f32(tc->zeros, 2048, 0.0f, s));
+    }
+    const RawTensor* w;
+    MRD_TRY(raw_need(c, bb + "conv1.weight", &w));
+    MRD_TRY(walloc(c, &tc->stem_w, 64 * 7 * 32));
+    float* dummy_bias = nullptr;
+    MRD_TRY(walloc(c, &dummy_bias, 2048));
+    MRD_TRY(pack_stem_bn(w->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, tc->stem_w, dummy_bias, s));
+    tc->bn_names.clear();
+    tc->bn_names.push_back(bb + "bn1");
+    tc->blocks.resize(c->blocks.size());
+    size_t bi = 0;
+    auto pack = [&](const std::string& conv, const ConvW& shape, ConvW* out) -> int {
+        const RawTensor* cw;
+        MRD_TRY(raw_need(c, conv + ".weight", &cw));
+        *out = ConvW(shape);
+        out->w = nullptr;
+        out->b = tc->zeros;
+        MRD_TRY(walloc(c, &out->w, cw->numel()));
+        float* scratch_bias = dummy_bias;
+        return pack_conv_bn(cw->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, shape.cout, shape.cin, shape.k,
+                            out->w, scratch_bias, s);
+    };
+    for (int L = 1; L <= 4 && bi < c->blocks.size(); ++L) {
+        for (int i = 0; bi < c->blocks.size(); ++i) {
+            char pre[96];
+            snprintf(pre, sizeof(pre), "%slayer%d.%d.", bb.c_str(), L, i);
+            const std::string p(pre);
+            if (c->raw.find(p + "conv1.weight") == c->raw.end()) break;
+            const Bottleneck& src = c->blocks[bi];
+            Bottleneck& dst = tc->blocks[bi];
+            // keep previously allocated filters (re-pack in place)
+            ConvW keep1 = dst.c1, keep2 = dst.c2, keep3 = dst.c3, keepd = dst.ds;
+            auto pack_keep = [&](const std::string& conv, const ConvW& shape, ConvW* out, const ConvW& keep) -> int {
+                const RawTensor* cw;
+                MRD_TRY(raw_need(c, conv + ".weight", &cw));
+                bf16* wbuf = keep.w;
+                *out = ConvW(shape);
+                out->w = wbuf;
+                out->b = tc->zeros;
+                MRD_TRY(walloc(c, &out->w, cw->numel()));
+                return pack_conv_bn(cw->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, shape.cout, shape.cin,
+                                    shape.k, out->w, dummy_bias, s);
+            };
+            MRD_TRY(pack_keep(p + "conv1", src.c1, &dst.c1, keep1));
+            MRD_TRY(pack_keep(p + "conv2", src.c2, &dst.c2, keep2));
+            MRD_TRY(pack_keep(p + "conv3", src.c3, &dst.c3, keep3));
+            dst.has_ds = src.has_ds;
+            tc->bn_names.push_back(p + "bn1");
+            tc->bn_names.push_back(p + "bn2");
+            tc->bn_names.push_back(p + "bn3");
+            if (src.has_ds) {
+                MRD_TRY(pack_keep(p + "downsample.0", src.ds, &dst.ds, keepd));
+                tc->bn_names.push_back(p + "downsample.1");
+            }
+            ++bi;
+        }
+    }
+    (void)pack;
+    if (!tc->stats) MRD_TRY(walloc(c, &tc->stats, static_cast<long long>(tc->bn_names.size()) * 4 * 2048));
+    tc->packed = true;
+    tc->B = 0;  // filters may have moved: re-plan
+    return 0;
+}
+
+int train_cnn_plan(mrd_ctx* c, int B, int H, int W) {
+    TrainCnn* tc = train_cnn(c);
+    if (tc->B == B && tc->H == H && tc->W == W && tc->ws_epoch == c->cnn_ws_epoch) return 0;
+    CnnPlan p;
+    p.B = B; p.H = H; p.W = W;
+    MRD_TRY(plan_stem(&p.stem, c->xpad, B, H, W, tc->stem_w, tc->zeros, c->stem_out, ACT_NONE));
+    int h = H / 4, w = W / 4;
+    const bf16* x = c->act0;
+    bf16* bufs[2] = {c->act0, c->act1};
+    int cur = 0;
+    p.blocks.resize(tc->blocks.size());
+    for (size_t i = 0; i < tc->blocks.size(); ++i) {
+        const Bottleneck& b = tc->blocks[i];
+        CnnPlan::BlockPlan& bp = p.blocks[i];
+        const int ho = h / b.c2.stride, wo = w / b.c2.stride;
+        bf16* y = bufs[cur ^ 1];
+        MRD_TRY(plan_conv(&bp.c1, x, B, h, w, b.c1.cin, b.c1.w, b.c1.cout, b.c1.k, 1, b.c1.b, c->mid0, nullptr, ACT_NONE));
+        MRD_TRY(plan_conv(&bp.c2, c->mid0, B, h, w, b.c2.cin, b.c2.w, b.c2.cout, b.c2.k, b.c2.stride, b.c2.b, c->mid1,
+                          nullptr, ACT_NONE));
+        bp.has_ds = b.has_ds;
+        if (b.has_ds)
+            MRD_TRY(plan_conv(&bp.ds, x, B, h, w, b.ds.cin, b.ds.w, b.ds.cout, b.ds.k, b.ds.stride, b.ds.b, c->dsb,
+                              nullptr, ACT_NONE));
+        MRD_TRY(plan_conv(&bp.c3, c->mid1, B, ho, wo, b.c3.cin, b.c3.w, b.c3.cout, b.c3.k, 1, b.c3.b, y, nullptr, ACT_NONE));
+        x = y;
+        cur ^= 1;
+        h = ho;
+        w = wo;
+    }
+    p.final_act = x;
+    p.final_hw = h * w;
+    tc->plan = std::move(p);
+    tc->B = B; tc->H = H; tc->W = W;
+    tc->ws_epoch = c->cnn_ws_epoch;
+    return 0;
+}
+
+int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int H, int W, float* pooled_f32,
+                       cudaStream_t s) {
+    if (img_dtype != MRD_DT_F32 && img_dtype != MRD_DT_BF16) {
+        set_last_error("images must be f32 or bf16 (dtype code %d)", img_dtype);
+        return -1;
+    }
+    if (H % 32 != 0 || W % 32 != 0 || H <= 0 || W <= 0) {
+        set_last_error("image size %dx%d unsupported: H and W must be multiples of 32", H, W);
+        return -1;
+    }
+    TrainState* t = train_state(c);
+    MRD_TRY(ensure_cnn_ws(c, H, W));
+    MRD_TRY(train_cnn_pack(c, s));
+    MRD_TRY(train_cnn_plan(c, B, H, W));
+    TrainCnn* tc = t->cnn;
+    const size_t n_sites = tc->bn_names.size();
+    cudaError_t e = cudaMemsetAsync(tc->stats, 0, sizeof(float) * n_sites * 4 * 2048, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(bn stats)");
+    size_t site = 0;
+    auto bn = [&](bf16* y, long long rows, int C, const bf16* identity, int relu) -> int {
+        const std::string& nm = tc->bn_names[site];
+        float* st = tc->stats + site * 4 * 2048;
+        ++site;
+        const RawTensor *g, *b, *rm, *rv;
+        MRD_TRY(raw_need(c, nm + ".weight", &g));
+        MRD_TRY(raw_need(c, nm + ".bias", &b));
+        MRD_TRY(raw_need(c, nm + ".running_mean", &rm));
+        MRD_TRY(raw_need(c, nm + ".running_var", &rv));
+        MRD_TRY(bn_stats_bf16(y, rows, C, st, st + 2048, s));
+        MRD_TRY(bn_finalize(st, st + 2048, rows, C, g->p, b->p, c->bn_eps, static_cast<float>(t->o.bn_momentum),
+                            const_cast<float*>(rm->p), const_cast<float*>(rv->p), st + 4096, st + 6144, s));
+        c->launches += 3;
+        return bn_apply_bf16(y, rows, C, st + 4096, st + 6144, identity, relu, s);
+    };
+    const CnnPlan& p = tc->plan;
+    MRD_TRY(repack_images(images, img_dtype == MRD_DT_BF16, B, H, W, c->xpad, s));
+    MRD_TRY(run(c, "train.conv_stem", p.stem, s));
+    MRD_TRY(bn(c->stem_out, 1LL * B * (H / 2) * (W / 2), 64, nullptr, 1));
+    MRD_TRY(maxpool3x3s2(c->stem_out, B, H / 2, W / 2, 64, c->act0, s));
+    c->launches += 2;
+    int h = H / 4, w = W / 4;
+    bf16* bufs[2] = {c->act0, c->act1};
+    int cur = 0;
+    for (size_t i = 0; i < p.blocks.size(); ++i) {
+        const Bottleneck& b = tc->blocks[i];
+        const CnnPlan::BlockPlan& bp = p.blocks[i];
+        const int ho = h / b.c2.stride, wo = w / b.c2.stride;
+        bf16* x = bufs[cur];
+        bf16* y = bufs[cur ^ 1];
+        MRD_TRY(run(c, "train.conv", bp.c1, s));
+        MRD_TRY(bn(c->mid0, 1LL * B * h * w, b.c1.cout, nullptr, 1));
+        MRD_TRY(run(c, "train.conv", bp.c2, s));
+        MRD_TRY(bn(c->mid1, 1LL * B * ho * wo, b.c2.cout, nullptr, 1));
+        MRD_TRY(run(c, "train.conv", bp.c3, s));
+        // bn_names order per block: bn1, bn2, bn3, downsample.1 - run bn3's statistics before the downsample
+        // branch but apply it after (it needs the identity)
+        const bf16* identity = x;
+        if (bp.has_ds) {
+            const size_t site_bn3 = site;
+            ++site;   // reserve bn3, do the downsample site first
+            MRD_TRY(run(c, "train.conv", bp.ds, s));
+            MRD_TRY(bn(c->dsb, 1LL * B * ho * wo, b.ds.cout, nullptr, 0));
+            const size_t after = site;
+            site = site_bn3;
+            MRD_TRY(bn(y, 1LL * B * ho * wo, b.c3.cout, c->dsb, 1));
+            site = after;
+        } else {
+            MRD_TRY(bn(y, 1LL * B * ho * wo, b.c3.cout, identity, 1));
+        }
+        cur ^= 1;
+        h = ho;
+        w = wo;
+    }
+    MRD_TRY(global_avgpool(p.final_act, B, p.final_hw, c->feat_dim, c->b_pooled, pooled_f32, s));
+    ++c->launches;
+    return 0;
+}
+
+void train_cnn_invalidate(TrainState* t) {
+    if (t->cnn) t->cnn->packed = false;
+}
+void train_cnn_free(TrainState* t) {
+    delete t->cnn;   // device buffers are weight allocations of the context (freed with it)
+    t->cnn = nullptr;
+}
+
 typedef std::unordered_map<std::string, float*> GradTable;
 inline float* grad_of(const GradTable& g, const std::string& k) {
     auto it = g.find(k);
@@ -329,11 +558,6 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         set_last_error("training step: classifier activation must be relu");
         return -1;
     }
-    if (o.bn_train) {
-        set_last_error("training step: batch-statistics BatchNorm is not implemented; put the (frozen) backbone in "
-                       "eval mode");
-        return -1;
-    }
     const int Hd = c->hidden, F = c->ffn, Fd = c->fusion_dim;
     MRD_TRY(ensure_batch_ws(c, B));
     MRD_TRY(ensure_text_ws(c, B * S, B));
@@ -345,7 +569,10 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     const int T = B * S;
 
     // ---- image branch: frozen backbone (forward only), then the trainable projection in fp32
-    MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, nullptr, s));
+    if (o.bn_train)
+        MRD_TRY(run_backbone_train(c, images, img_dtype, B, H, W, t->pooled, s));
+    else
+        MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, nullptr, s));
     MRD_TRY(lin_fwd(c, "cnn_encoder.projection.0", t->pooled, c->feat_dim, B, t->a1, c->proj1.out, MRD_ACT_RELU,
                     nullptr, 0, s));
     MRD_TRY(dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));

@@ -464,6 +464,76 @@ embed_ln_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ r
     }
 }
 
+// ------------------------------------------------------------------ BatchNorm (batch statistics)
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const bf16* __restrict__ y, long long rows, int C, float* __restrict__ sum,
+                float* __restrict__ sumsq) {
+    __shared__ float red[2][8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + lane * 2;
+    float a0 = 0.0f, a1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    if (c < C) {
+        for (long long r = static_cast<long long>(blockIdx.y) * 8 + warp; r < rows;
+             r += static_cast<long long>(gridDim.y) * 8) {
+            const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(y + r * C + c));
+            a0 += v.x; a1 += v.y;
+            q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+        }
+    }
+    red[0][warp][lane * 2] = a0; red[0][warp][lane * 2 + 1] = a1;
+    red[1][warp][lane * 2] = q0; red[1][warp][lane * 2 + 1] = q1;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[which][w][col];
+        const int cc = blockIdx.x * 64 + col;
+        if (cc < C) atomicAdd((which ? sumsq : sum) + cc, t);
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float n, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = sum[c] / n;
+    const float var = fmaxf(sumsq[c] / n - mean * mean, 0.0f);
+    const float sc = gamma[c] * rsqrtf(var + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * (n / fmaxf(n - 1.0f, 1.0f));
+}
+
+__global__ void bn_apply_kernel(bf16* __restrict__ y, long long n8, int C, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const bf16* __restrict__ identity, int relu) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>((i * 8) % C);
+        float v[8];
+        unpack8(reinterpret_cast<const uint4*>(y)[i], v);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+        v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+        v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+        if (identity) {
+            float r[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(identity) + i), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        reinterpret_cast<uint4*>(y)[i] = pack8(v);
+    }
+}
+
 // ------------------------------------------------------------------ transposed weight pack
 __global__ void __launch_bounds__(256)
 pack_linear_t_kernel(const float* __restrict__ w, int rows, int cols, float scale, bf16* __restrict__ out,
@@ -643,6 +713,41 @@ int embed_ln_bwd(const long long* ids, const int* row_tok, int rows, const int* 
     embed_ln_bwd_kernel<<<grid, 256, 0, s>>>(ids, row_tok, rows, dyn_rows, S, word, pos_type, gamma, eps, vocab,
                                              pad_idx, dy, dword, dpos, dtype0, dgamma, dbeta);
     return check_launch("embed_ln_bwd");
+}
+
+int bn_stats_bf16(const bf16* y, long long rows, int C, float* sum, float* sumsq, cudaStream_t s) {
+    if (rows <= 0 || C <= 0) return 0;
+    if (C % 2) {
+        set_last_error("bn_stats_bf16: odd channel count");
+        return -1;
+    }
+    long long split = (rows + 511) / 512;
+    if (split > 148 * 8) split = 148 * 8;
+    if (split < 1) split = 1;
+    dim3 grid((C + 63) / 64, static_cast<unsigned>(split));
+    bn_stats_kernel<<<grid, 256, 0, s>>>(y, rows, C, sum, sumsq);
+    return check_launch("bn_stats_bf16");
+}
+int bn_finalize(const float* sum, const float* sumsq, long long n, int C, const float* gamma, const float* beta,
+                float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                cudaStream_t s) {
+    if (C <= 0) return 0;
+    bn_finalize_kernel<<<nblk(C, 128), 128, 0, s>>>(sum, sumsq, static_cast<float>(n), C, gamma, beta, eps, momentum,
+                                                  running_mean, running_var, scale, shift);
+    return check_launch("bn_finalize");
+}
+int bn_apply_bf16(bf16* y, long long rows, int C, const float* scale, const float* shift, const bf16* identity,
+                  int relu, cudaStream_t s) {
+    if (rows <= 0 || C <= 0) return 0;
+    if (C % 8) {
+        set_last_error("bn_apply_bf16: C %% 8 != 0");
+        return -1;
+    }
+    const long long n8 = rows * C / 8;
+    unsigned grid = nblk(n8, 256);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    bn_apply_kernel<<<grid, 256, 0, s>>>(y, n8, C, scale, shift, identity, relu);
+    return check_launch("bn_apply_bf16");
 }
 
 int pack_linear_t(const float* w, int rows, int cols, float scale, bf16* out, long long ld_out, int col_off,

@@ -90,6 +90,18 @@ int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const
                        const float* mask_bias, const int* seq_off, int B, int S, int heads, DropCfg d,
                        __nv_bfloat16* dqkv, cudaStream_t s);
 
+// ---- BatchNorm with batch statistics (frozen backbone under model.train(), TV:models/resnet.py:143-163) --
+// sum[c] += sum_r y[r,c], sumsq[c] += sum_r y[r,c]^2 over an NHWC bf16 tensor viewed as [rows, C]; C % 2 == 0.
+int bn_stats_bf16(const __nv_bfloat16* y, long long rows, int C, float* sum, float* sumsq, cudaStream_t s);
+// mean = sum/n, var = sumsq/n - mean^2 (biased); scale = gamma*rsqrt(var+eps), shift = beta - mean*scale;
+// running_mean/var (optional, the caller's nn.BatchNorm2d buffers) <- (1-m)*running + m*(mean, var*n/(n-1)).
+int bn_finalize(const float* sum, const float* sumsq, long long n, int C, const float* gamma, const float* beta,
+                float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                cudaStream_t s);
+// y = act(y*scale[c] + shift[c] (+ identity)) in place on [rows, C] bf16; C % 8 == 0.
+int bn_apply_bf16(__nv_bfloat16* y, long long rows, int C, const float* scale, const float* shift,
+                  const __nv_bfloat16* identity, int relu, cudaStream_t s);
+
 // w [rows, cols] fp32 -> out[c][col_off + r] = bf16(w[r][c] * scale), out row stride ld_out: the
 // transposed (input-major) copy of an nn.Linear weight used as the B operand of dX = dY W.
 int pack_linear_t(const float* w, int rows, int cols, float scale, __nv_bfloat16* out, long long ld_out,
