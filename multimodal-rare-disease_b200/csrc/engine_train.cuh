@@ -16,6 +16,13 @@
 //   * projection / fusion / head (rows = batch size): fp32 SIMT GEMMs (simt_gemm.cu) both ways.
 // Dropout masks are counter-based (rng.cuh) and recomputed in the backward pass.
 
+// a non-GEMM kernel of the training step: counted, and timed when the context is in profile mode
+#define TRK(label, cat, call)                        \
+    do {                                             \
+        ProfScope ps__(c, s, label, cat, 0.0, 0.0);  \
+        MRD_TRY(call);                               \
+    } while (0)
+
 struct TrainOpts {
     double p_bert_hidden = 0.1, p_bert_attn = 0.1, p_text_out = 0.1, p_cnn_proj = 0.5, p_fusion = 0.3,
            p_head = 0.5;
@@ -149,12 +156,12 @@ int train_ensure_packs(mrd_ctx* c, cudaStream_t s) {
         MRD_TRY(raw_need(c, p + "intermediate.dense.weight", &w1));
         MRD_TRY(raw_need(c, p + "output.dense.weight", &w2));
         // qkv_t: [Hd(in)][3*Hd(out)]; the query block carries the folded 1/sqrt(64) like the forward pack
-        MRD_TRY(pack_linear_t(wq->p, Hd, Hd, 0.125f, w.qkv_t, 3LL * Hd, 0, s));
-        MRD_TRY(pack_linear_t(wk->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, Hd, s));
-        MRD_TRY(pack_linear_t(wv->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, 2 * Hd, s));
-        MRD_TRY(pack_linear_t(wo->p, Hd, Hd, 1.0f, w.o_t, Hd, 0, s));
-        MRD_TRY(pack_linear_t(w1->p, F, Hd, 1.0f, w.f1_t, F, 0, s));     // W1 [F,Hd] -> [Hd][F]
-        MRD_TRY(pack_linear_t(w2->p, Hd, F, 1.0f, w.f2_t, Hd, 0, s));    // W2 [Hd,F] -> [F][Hd]
+        TRK("train.pack", CAT_MEM, pack_linear_t(wq->p, Hd, Hd, 0.125f, w.qkv_t, 3LL * Hd, 0, s));
+        TRK("train.pack", CAT_MEM, pack_linear_t(wk->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, Hd, s));
+        TRK("train.pack", CAT_MEM, pack_linear_t(wv->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, 2 * Hd, s));
+        TRK("train.pack", CAT_MEM, pack_linear_t(wo->p, Hd, Hd, 1.0f, w.o_t, Hd, 0, s));
+        TRK("train.pack", CAT_MEM, pack_linear_t(w1->p, F, Hd, 1.0f, w.f1_t, F, 0, s));     // W1 [F,Hd] -> [Hd][F]
+        TRK("train.pack", CAT_MEM, pack_linear_t(w2->p, Hd, F, 1.0f, w.f2_t, Hd, 0, s));    // W2 [Hd,F] -> [F][Hd]
     }
     t->packs_valid = true;
     return 0;
@@ -268,6 +275,7 @@ struct TrainCnn {
     bool packed = false;
     bf16* stem_w = nullptr;
     float *ones = nullptr, *zeros = nullptr;     // [2048] identity BatchNorm for the packers / zero bias
+    float* dummy_bias = nullptr;                 // [2048] bias output of the packers (always zero, unused)
     std::vector<Bottleneck> blocks;              // raw (un-folded) filters
     float* stats = nullptr;                      // [sites][4][2048]: sum, sumsq, scale, shift
     std::vector<std::string> bn_names;           // site -> "cnn_encoder.backbone....bnX"
@@ -295,24 +303,13 @@ int train_cnn_pack(mrd_ctx* c, cudaStream_t s) {
     const RawTensor* w;
     MRD_TRY(raw_need(c, bb + "conv1.weight", &w));
     MRD_TRY(walloc(c, &tc->stem_w, 64 * 7 * 32));
-    float* dummy_bias = nullptr;
-    MRD_TRY(walloc(c, &dummy_bias, 2048));
-    MRD_TRY(pack_stem_bn(w->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, tc->stem_w, dummy_bias, s));
+    MRD_TRY(walloc(c, &tc->dummy_bias, 2048));
+    float* dummy_bias = tc->dummy_bias;
+    TRK("train.pack", CAT_MEM, pack_stem_bn(w->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, tc->stem_w, dummy_bias, s));
     tc->bn_names.clear();
     tc->bn_names.push_back(bb + "bn1");
     tc->blocks.resize(c->blocks.size());
     size_t bi = 0;
-    auto pack = [&](const std::string& conv, const ConvW& shape, ConvW* out) -> int {
-        const RawTensor* cw;
-        MRD_TRY(raw_need(c, conv + ".weight", &cw));
-        *out = ConvW(shape);
-        out->w = nullptr;
-        out->b = tc->zeros;
-        MRD_TRY(walloc(c, &out->w, cw->numel()));
-        float* scratch_bias = dummy_bias;
-        return pack_conv_bn(cw->p, tc->ones, tc->zeros, tc->zeros, tc->ones, 0.0f, shape.cout, shape.cin, shape.k,
-                            out->w, scratch_bias, s);
-    };
     for (int L = 1; L <= 4 && bi < c->blocks.size(); ++L) {
         for (int i = 0; bi < c->blocks.size(); ++i) {
             char pre[96];
@@ -348,7 +345,6 @@ int train_cnn_pack(mrd_ctx* c, cudaStream_t s) {
             ++bi;
         }
     }
-    (void)pack;
     if (!tc->stats) MRD_TRY(walloc(c, &tc->stats, static_cast<long long>(tc->bn_names.size()) * 4 * 2048));
     tc->packed = true;
     tc->B = 0;  // filters may have moved: re-plan
@@ -420,18 +416,17 @@ int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int
         MRD_TRY(raw_need(c, nm + ".bias", &b));
         MRD_TRY(raw_need(c, nm + ".running_mean", &rm));
         MRD_TRY(raw_need(c, nm + ".running_var", &rv));
-        MRD_TRY(bn_stats_bf16(y, rows, C, st, st + 2048, s));
-        MRD_TRY(bn_finalize(st, st + 2048, rows, C, g->p, b->p, c->bn_eps, static_cast<float>(t->o.bn_momentum),
+        TRK("train.bn_stats", CAT_MEM, bn_stats_bf16(y, rows, C, st, st + 2048, s));
+        TRK("train.bn_finalize", CAT_MEM, bn_finalize(st, st + 2048, rows, C, g->p, b->p, c->bn_eps, static_cast<float>(t->o.bn_momentum),
                             const_cast<float*>(rm->p), const_cast<float*>(rv->p), st + 4096, st + 6144, s));
-        c->launches += 3;
-        return bn_apply_bf16(y, rows, C, st + 4096, st + 6144, identity, relu, s);
+        TRK("train.bn_apply", CAT_MEM, bn_apply_bf16(y, rows, C, st + 4096, st + 6144, identity, relu, s));
+        return 0;
     };
     const CnnPlan& p = tc->plan;
-    MRD_TRY(repack_images(images, img_dtype == MRD_DT_BF16, B, H, W, c->xpad, s));
+    TRK("train.repack_images", CAT_MEM, repack_images(images, img_dtype == MRD_DT_BF16, B, H, W, c->xpad, s));
     MRD_TRY(run(c, "train.conv_stem", p.stem, s));
     MRD_TRY(bn(c->stem_out, 1LL * B * (H / 2) * (W / 2), 64, nullptr, 1));
-    MRD_TRY(maxpool3x3s2(c->stem_out, B, H / 2, W / 2, 64, c->act0, s));
-    c->launches += 2;
+    TRK("train.maxpool", CAT_MEM, maxpool3x3s2(c->stem_out, B, H / 2, W / 2, 64, c->act0, s));
     int h = H / 4, w = W / 4;
     bf16* bufs[2] = {c->act0, c->act1};
     int cur = 0;
@@ -465,8 +460,7 @@ int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int
         h = ho;
         w = wo;
     }
-    MRD_TRY(global_avgpool(p.final_act, B, p.final_hw, c->feat_dim, c->b_pooled, pooled_f32, s));
-    ++c->launches;
+    TRK("train.avgpool", CAT_MEM, global_avgpool(p.final_act, B, p.final_hw, c->feat_dim, c->b_pooled, pooled_f32, s));
     return 0;
 }
 
@@ -496,8 +490,8 @@ int lin_fwd(mrd_ctx* c, const std::string& name, const float* x, long long ldx, 
     g.M = M; g.N = static_cast<int>(w->d[0]); g.K = static_cast<int>(w->d[1]);
     g.C = y; g.ldc = ldy;
     g.bias = b->p; g.act = act; g.res = res; g.ldr = ldr;
-    ++c->launches;
-    return simt_gemm(g, s);
+    TRK("train.simt_gemm", CAT_TENSOR, simt_gemm(g, s));
+    return 0;
 }
 
 // y = x W^T + b.  dW += dy^T x, db += colsum(dy) (when the parameter has a gradient slot);
@@ -514,12 +508,10 @@ int lin_bwd(mrd_ctx* c, const GradTable& gt, const std::string& name, const floa
         g.B = x; g.b_rs = 1; g.b_cs = ldx;
         g.M = N; g.N = K; g.K = M;
         g.C = gw; g.ldc = K; g.accumulate = 1;
-        ++c->launches;
-        MRD_TRY(simt_gemm(g, s));
+        TRK("train.simt_gemm", CAT_TENSOR, simt_gemm(g, s));
     }
     if (float* gb = grad_of(gt, name + ".bias")) {
-        ++c->launches;
-        MRD_TRY(colsum_f32(dy, lddy, M, N, gb, s));
+        TRK("train.colsum", CAT_MEM, colsum_f32(dy, lddy, M, N, gb, s));
     }
     if (dx) {
         SimtGemm g;  // C[m, k_in] = sum_n dy[m, n] * W[n, k_in]
@@ -528,8 +520,7 @@ int lin_bwd(mrd_ctx* c, const GradTable& gt, const std::string& name, const floa
         g.M = M; g.N = K; g.K = N;
         g.C = dx; g.ldc = lddx;
         g.res = dx_res; g.ldr = ld_res;
-        ++c->launches;
-        MRD_TRY(simt_gemm(g, s));
+        TRK("train.simt_gemm", CAT_TENSOR, simt_gemm(g, s));
     }
     return 0;
 }
@@ -575,19 +566,17 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, nullptr, s));
     MRD_TRY(lin_fwd(c, "cnn_encoder.projection.0", t->pooled, c->feat_dim, B, t->a1, c->proj1.out, MRD_ACT_RELU,
                     nullptr, 0, s));
-    MRD_TRY(dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));
     MRD_TRY(lin_fwd(c, "cnn_encoder.projection.3", t->p1, c->proj1.out, B, t->img, c->proj2.out, MRD_ACT_NONE,
                     nullptr, 0, s));
-    c->launches += 1;
 
     // ---- text branch
-    MRD_TRY(compact_tokens(mask, mask_dtype, B, S, 0, c->t_seq_off, c->t_row_tok, c->t_bias, c->t_nrows,
+    TRK("train.compact_tokens", CAT_MEM, compact_tokens(mask, mask_dtype, B, S, 0, c->t_seq_off, c->t_row_tok, c->t_bias, c->t_nrows,
                            c->t_scratch, s));
-    MRD_TRY(bert_embed_layernorm(ids, B, S, c->word_emb, c->pos_type, c->emb_g, c->emb_b, c->bert_ln_eps, c->vocab,
+    TRK("train.embed_ln", CAT_MEM, bert_embed_layernorm(ids, B, S, c->word_emb, c->pos_type, c->emb_g, c->emb_b, c->bert_ln_eps, c->vocab,
                                  t->L[0].x, s, c->t_row_tok, c->t_nrows));
-    MRD_TRY(dropout_bf16(t->L[0].x, Hd, T, Hd, c->t_nrows, make_drop(seed, SITE_EMB, o.p_bert_hidden), t->L[0].x,
+    TRK("train.dropout", CAT_MEM, dropout_bf16(t->L[0].x, Hd, T, Hd, c->t_nrows, make_drop(seed, SITE_EMB, o.p_bert_hidden), t->L[0].x,
                          Hd, s));
-    c->launches += 5;
     const size_t nl = c->layers.size();
     for (size_t i = 0; i < nl; ++i) {
         const BertLayerW& Lw = c->layers[i];
@@ -596,21 +585,19 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         bf16* x_next = i + 1 < nl ? t->L[i + 1].x : t->x_final;
         MRD_TRY(run(c, "train.qkv", p.qkv, s));
         const DropCfg da = make_drop(seed, site_attn(i), o.p_bert_attn);
-        MRD_TRY(attention_forward(b.qkv, c->t_bias, c->t_seq_off, B, S, c->bert_heads, b.ctx, s, T, 0, &da));
+        TRK("train.attention", CAT_ATTN, attention_forward(b.qkv, c->t_bias, c->t_seq_off, B, S, c->bert_heads, b.ctx, s, T, 0, &da));
         MRD_TRY(run(c, "train.attn_out", p.o, s));
-        MRD_TRY(drop_add_ln_fwd(t->z, b.x, T, Hd, c->t_nrows, make_drop(seed, site_attn_out(i), o.p_bert_hidden),
+        TRK("train.drop_add_ln", CAT_MEM, drop_add_ln_fwd(t->z, b.x, T, Hd, c->t_nrows, make_drop(seed, site_attn_out(i), o.p_bert_hidden),
                                 Lw.ln1g, Lw.ln1b, c->bert_ln_eps, b.s1, b.h1, s));
         MRD_TRY(run(c, "train.ffn1", p.f1, s));
-        MRD_TRY(gelu_fwd_bf16(b.u, T, F, c->t_nrows, b.g, s));
+        TRK("train.gelu", CAT_MEM, gelu_fwd_bf16(b.u, T, F, c->t_nrows, b.g, s));
         MRD_TRY(run(c, "train.ffn2", p.f2, s));
-        MRD_TRY(drop_add_ln_fwd(t->z, b.h1, T, Hd, c->t_nrows, make_drop(seed, site_ffn_out(i), o.p_bert_hidden),
+        TRK("train.drop_add_ln", CAT_MEM, drop_add_ln_fwd(t->z, b.h1, T, Hd, c->t_nrows, make_drop(seed, site_ffn_out(i), o.p_bert_hidden),
                                 Lw.ln2g, Lw.ln2b, c->bert_ln_eps, b.s2, x_next, s));
-        c->launches += 4;
     }
     // CLS row (src/text_encoder.py:118) + TextEncoder.dropout
-    MRD_TRY(gather_cls_rows_f32(t->x_final, c->t_seq_off, B, Hd, t->cls, s));
-    MRD_TRY(dropout_f32(t->cls, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), t->txt, s));
-    c->launches += 2;
+    TRK("train.cls", CAT_MEM, gather_cls_rows_f32(t->x_final, c->t_seq_off, B, Hd, t->cls, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(t->cls, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), t->txt, s));
 
     // ---- fusion (src/fusion_model.py:245-291 in train mode)
     const std::string f = "fusion.fusion_layer.";
@@ -618,19 +605,18 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     MRD_TRY(lin_fwd(c, f + "image_proj", t->img, c->fusion_img_in, B, t->ip, Fd, MRD_ACT_NONE, nullptr, 0, s));
     MRD_TRY(lin_fwd(c, f + "text_proj", t->txt, c->fusion_txt_in, B, t->tp, Fd, MRD_ACT_NONE, nullptr, 0, s));
     MRD_TRY(lin_fwd(c, f + "image_to_text_attention.value_proj", t->tp, Fd, B, t->v1, Fd, MRD_ACT_NONE, nullptr, 0, s));
-    MRD_TRY(head_dropout_f32(t->v1, B, c->fusion_heads, hd, make_drop(seed, SITE_I2T, o.p_fusion), t->v1d, nullptr, s));
+    TRK("train.dropout", CAT_MEM, head_dropout_f32(t->v1, B, c->fusion_heads, hd, make_drop(seed, SITE_I2T, o.p_fusion), t->v1d, nullptr, s));
     MRD_TRY(lin_fwd(c, f + "image_to_text_attention.output_proj", t->v1d, Fd, B, t->pre_i, Fd, MRD_ACT_NONE,
                     c->fusion_residual ? t->ip : nullptr, Fd, s));
     MRD_TRY(lin_fwd(c, f + "text_to_image_attention.value_proj", t->ip, Fd, B, t->v2, Fd, MRD_ACT_NONE, nullptr, 0, s));
-    MRD_TRY(head_dropout_f32(t->v2, B, c->fusion_heads, hd, make_drop(seed, SITE_T2I, o.p_fusion), t->v2d, nullptr, s));
+    TRK("train.dropout", CAT_MEM, head_dropout_f32(t->v2, B, c->fusion_heads, hd, make_drop(seed, SITE_T2I, o.p_fusion), t->v2d, nullptr, s));
     MRD_TRY(lin_fwd(c, f + "text_to_image_attention.output_proj", t->v2d, Fd, B, t->pre_t, Fd, MRD_ACT_NONE,
                     c->fusion_residual ? t->tp : nullptr, Fd, s));
-    MRD_TRY(ln_fwd_f32(t->pre_i, Fd, c->ln_i_g, c->ln_i_b, c->fusion_ln_eps, B, Fd, t->cat, 2 * Fd, s));
-    MRD_TRY(ln_fwd_f32(t->pre_t, Fd, c->ln_t_g, c->ln_t_b, c->fusion_ln_eps, B, Fd, t->cat + Fd, 2 * Fd, s));
+    TRK("train.ln_f32", CAT_MEM, ln_fwd_f32(t->pre_i, Fd, c->ln_i_g, c->ln_i_b, c->fusion_ln_eps, B, Fd, t->cat, 2 * Fd, s));
+    TRK("train.ln_f32", CAT_MEM, ln_fwd_f32(t->pre_t, Fd, c->ln_t_g, c->ln_t_b, c->fusion_ln_eps, B, Fd, t->cat + Fd, 2 * Fd, s));
     MRD_TRY(lin_fwd(c, f + "fusion.0", t->cat, 2 * Fd, B, t->g0, Fd, MRD_ACT_RELU, nullptr, 0, s));
-    MRD_TRY(dropout_f32(t->g0, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->fh, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->fh, s));
     MRD_TRY(lin_fwd(c, f + "fusion.3", t->fh, Fd, B, t->fused, Fd, MRD_ACT_NONE, nullptr, 0, s));
-    c->launches += 5;
 
     // ---- head (src/multimodal_classifier.py:73-83)
     const float* x = t->fused;
@@ -640,8 +626,7 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         snprintf(nm, sizeof(nm), "classifier.classifier.%zu", 3 * j);
         const int n = c->head_hidden[j].out;
         MRD_TRY(lin_fwd(c, nm, x, ld, B, t->g0, n, MRD_ACT_RELU, nullptr, 0, s));
-        MRD_TRY(dropout_f32(t->g0, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(j), o.p_head), t->hh[j], s));
-        ++c->launches;
+        TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(j), o.p_head), t->hh[j], s));
         x = t->hh[j];
         ld = n;
     }
@@ -658,9 +643,8 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
 // dW = dY^T X through the tcgen05 GEMM: stage both operands token-minor, fp32 result into `dst`.
 int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* dY, int n_out, const bf16* X, int n_in,
                 float* dst, cudaStream_t s) {
-    MRD_TRY(transpose_pad_bf16(dY, n_out, t->Ta, n_out, c->t_nrows, t->At, t->Tp, s));
-    MRD_TRY(transpose_pad_bf16(X, n_in, t->Ta, n_in, c->t_nrows, t->Bt, t->Tp, s));
-    c->launches += 2;
+    TRK("train.transpose", CAT_MEM, transpose_pad_bf16(dY, n_out, t->Ta, n_out, c->t_nrows, t->At, t->Tp, s));
+    TRK("train.transpose", CAT_MEM, transpose_pad_bf16(X, n_in, t->Ta, n_in, c->t_nrows, t->Bt, t->Tp, s));
     return run_f32(c, "train.wgrad", plan, dst, n_in, s);
 }
 
@@ -702,13 +686,12 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         snprintf(nm, sizeof(nm), "classifier.classifier.%zu", 3 * jj);
         const int n = c->head_hidden[jj].out;
         // dy is the gradient of the post-dropout activation hh[jj]
-        MRD_TRY(dropout_f32(dy, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(jj), o.p_head), t->g0, s));
-        MRD_TRY(relu_bwd_f32(t->hh[jj], t->g0, nB * n, t->g0, s));
+        TRK("train.dropout", CAT_MEM, dropout_f32(dy, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(jj), o.p_head), t->g0, s));
+        TRK("train.relu_bwd", CAT_MEM, relu_bwd_f32(t->hh[jj], t->g0, nB * n, t->g0, s));
         const float* x = jj ? t->hh[jj - 1] : t->fused;
         const int ldx = jj ? c->head_hidden[jj - 1].out : c->head_in;
         float* dx = ping[cur ^ 1];
         MRD_TRY(lin_bwd(c, gt, nm, x, ldx, t->g0, n, B, dx, ldx, nullptr, 0, s));
-        c->launches += 2;
         dy = dx;
         ldy = ldx;
         cur ^= 1;
@@ -717,30 +700,28 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
     const std::string f = "fusion.fusion_layer.";
     float* d_fh = ping[cur ^ 1];
     MRD_TRY(lin_bwd(c, gt, f + "fusion.3", t->fh, Fd, dy, ldy, B, d_fh, Fd, nullptr, 0, s));
-    MRD_TRY(dropout_f32(d_fh, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->g0, s));
-    MRD_TRY(relu_bwd_f32(t->fh, t->g0, nB * Fd, t->g0, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(d_fh, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->g0, s));
+    TRK("train.relu_bwd", CAT_MEM, relu_bwd_f32(t->fh, t->g0, nB * Fd, t->g0, s));
     float* d_cat = t->g3;  // [B, 2*Fd]
     MRD_TRY(lin_bwd(c, gt, f + "fusion.0", t->cat, 2 * Fd, t->g0, Fd, B, d_cat, 2 * Fd, nullptr, 0, s));
     float* d_pre_i = t->g1;
     float* d_pre_t = t->g2;
-    MRD_TRY(ln_bwd_f32(t->pre_i, Fd, d_cat, 2 * Fd, c->ln_i_g, c->fusion_ln_eps, B, Fd, d_pre_i, Fd,
+    TRK("train.ln_f32", CAT_MEM, ln_bwd_f32(t->pre_i, Fd, d_cat, 2 * Fd, c->ln_i_g, c->fusion_ln_eps, B, Fd, d_pre_i, Fd,
                        grad_of(gt, f + "layer_norm_image.weight"), grad_of(gt, f + "layer_norm_image.bias"), s));
-    MRD_TRY(ln_bwd_f32(t->pre_t, Fd, d_cat + Fd, 2 * Fd, c->ln_t_g, c->fusion_ln_eps, B, Fd, d_pre_t, Fd,
+    TRK("train.ln_f32", CAT_MEM, ln_bwd_f32(t->pre_t, Fd, d_cat + Fd, 2 * Fd, c->ln_t_g, c->fusion_ln_eps, B, Fd, d_pre_t, Fd,
                        grad_of(gt, f + "layer_norm_text.weight"), grad_of(gt, f + "layer_norm_text.bias"), s));
-    c->launches += 4;
     // pre_i = ip + O1(headdrop(V1(tp)));  pre_t = tp + O2(headdrop(V2(ip)))
     float* d_v = t->g0;      // gradient of the dropped value vector, then of the value vector
     float* d_ip = t->g3;     // d_cat is dead after the two LayerNorm backwards
     float* d_tp = t->g4;
     MRD_TRY(lin_bwd(c, gt, f + "image_to_text_attention.output_proj", t->v1d, Fd, d_pre_i, Fd, B, d_v, Fd, nullptr, 0, s));
-    MRD_TRY(head_dropout_f32(d_v, B, c->fusion_heads, hd, make_drop(seed, SITE_I2T, o.p_fusion), d_v, nullptr, s));
+    TRK("train.dropout", CAT_MEM, head_dropout_f32(d_v, B, c->fusion_heads, hd, make_drop(seed, SITE_I2T, o.p_fusion), d_v, nullptr, s));
     MRD_TRY(lin_bwd(c, gt, f + "image_to_text_attention.value_proj", t->tp, Fd, d_v, Fd, B, d_tp, Fd,
                     c->fusion_residual ? d_pre_t : nullptr, Fd, s));
     MRD_TRY(lin_bwd(c, gt, f + "text_to_image_attention.output_proj", t->v2d, Fd, d_pre_t, Fd, B, d_v, Fd, nullptr, 0, s));
-    MRD_TRY(head_dropout_f32(d_v, B, c->fusion_heads, hd, make_drop(seed, SITE_T2I, o.p_fusion), d_v, nullptr, s));
+    TRK("train.dropout", CAT_MEM, head_dropout_f32(d_v, B, c->fusion_heads, hd, make_drop(seed, SITE_T2I, o.p_fusion), d_v, nullptr, s));
     MRD_TRY(lin_bwd(c, gt, f + "text_to_image_attention.value_proj", t->ip, Fd, d_v, Fd, B, d_ip, Fd,
                     c->fusion_residual ? d_pre_i : nullptr, Fd, s));
-    c->launches += 2;
     float* d_img = t->g1;    // d_pre_i / d_pre_t are dead now
     float* d_txt = t->g2;
     MRD_TRY(lin_bwd(c, gt, f + "image_proj", t->img, c->fusion_img_in, d_ip, Fd, B, d_img, c->fusion_img_in, nullptr, 0, s));
@@ -749,20 +730,18 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
     // ---- image projection (the backbone below it is frozen)
     MRD_TRY(lin_bwd(c, gt, "cnn_encoder.projection.3", t->p1, c->proj1.out, d_img, c->proj2.out, B, t->g0,
                     c->proj1.out, nullptr, 0, s));
-    MRD_TRY(dropout_f32(t->g0, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->g0, s));
-    MRD_TRY(relu_bwd_f32(t->p1, t->g0, nB * c->proj1.out, t->g0, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->g0, s));
+    TRK("train.relu_bwd", CAT_MEM, relu_bwd_f32(t->p1, t->g0, nB * c->proj1.out, t->g0, s));
     MRD_TRY(lin_bwd(c, gt, "cnn_encoder.projection.0", t->pooled, c->feat_dim, t->g0, c->proj1.out, B, nullptr, 0,
                     nullptr, 0, s));
-    c->launches += 2;
 
     // ---- text branch: TextEncoder.dropout, CLS scatter, then the encoder layers in reverse
-    MRD_TRY(dropout_f32(d_txt, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), d_txt, s));
+    TRK("train.dropout", CAT_MEM, dropout_f32(d_txt, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), d_txt, s));
     const size_t nl = c->layers.size();
     bf16* dx_top = (nl & 1) ? t->dxb : t->dxa;   // layer nl-1 reads dx[nl & 1]
     cudaError_t e = cudaMemsetAsync(dx_top, 0, sizeof(bf16) * static_cast<size_t>(T) * Hd, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dX)");
-    MRD_TRY(scatter_cls_rows_bf16(d_txt, c->t_seq_off, B, Hd, dx_top, s));
-    c->launches += 3;
+    TRK("train.cls", CAT_MEM, scatter_cls_rows_bf16(d_txt, c->t_seq_off, B, Hd, dx_top, s));
     const std::string enc = "text_encoder.encoder.encoder.layer.";
     for (size_t i = nl; i-- > 0;) {
         const BertLayerW& Lw = c->layers[i];
@@ -773,33 +752,33 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         const DropCfg d_ffn = make_drop(seed, site_ffn_out(i), o.p_bert_hidden);
         const DropCfg d_att = make_drop(seed, site_attn_out(i), o.p_bert_hidden);
         // x_{i+1} = LN2(s2), s2 = h1 + drop(W2 g + b2)
-        MRD_TRY(ln_bwd_bf16(b.s2, dx_in, Lw.ln2g, c->bert_ln_eps, T, Hd, c->t_nrows, t->d_s,
+        TRK("train.ln_bwd", CAT_MEM, ln_bwd_bf16(b.s2, dx_in, Lw.ln2g, c->bert_ln_eps, T, Hd, c->t_nrows, t->d_s,
                             grad_of(gt, pre + "output.LayerNorm.weight"), grad_of(gt, pre + "output.LayerNorm.bias"), s));
         const bf16* dz = t->d_s;
         if (d_ffn.thresh) {
-            MRD_TRY(dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_ffn, t->dz, Hd, s));
+            TRK("train.dropout", CAT_MEM, dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_ffn, t->dz, Hd, s));
             dz = t->dz;
         }
         if (float* gw = grad_of(gt, pre + "output.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_f2, dz, Hd, b.g, F, gw, s));
-        if (float* gb = grad_of(gt, pre + "output.dense.bias")) MRD_TRY(colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
+        if (float* gb = grad_of(gt, pre + "output.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
         MRD_TRY(run(c, "train.dgrad", dz == t->dz ? p.d_g : p.d_g0, s));
-        MRD_TRY(gelu_bwd_bf16(b.u, t->dbig, T, F, c->t_nrows, t->dbig, s));
+        TRK("train.gelu_bwd", CAT_MEM, gelu_bwd_bf16(b.u, t->dbig, T, F, c->t_nrows, t->dbig, s));
         if (float* gw = grad_of(gt, pre + "intermediate.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_f1, t->dbig, F, b.h1, Hd, gw, s));
-        if (float* gb = grad_of(gt, pre + "intermediate.dense.bias")) MRD_TRY(colsum_bf16(t->dbig, F, T, F, c->t_nrows, 1.0f, gb, s));
+        if (float* gb = grad_of(gt, pre + "intermediate.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(t->dbig, F, T, F, c->t_nrows, 1.0f, gb, s));
         MRD_TRY(run(c, "train.dgrad", p.d_h1, s));   // dh1 = du W1 + d_s2
         // h1 = LN1(s1), s1 = x + drop(Wo ctx + bo)
-        MRD_TRY(ln_bwd_bf16(b.s1, t->dh1, Lw.ln1g, c->bert_ln_eps, T, Hd, c->t_nrows, t->d_s,
+        TRK("train.ln_bwd", CAT_MEM, ln_bwd_bf16(b.s1, t->dh1, Lw.ln1g, c->bert_ln_eps, T, Hd, c->t_nrows, t->d_s,
                             grad_of(gt, pre + "attention.output.LayerNorm.weight"),
                             grad_of(gt, pre + "attention.output.LayerNorm.bias"), s));
         dz = t->d_s;
         if (d_att.thresh) {
-            MRD_TRY(dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_att, t->dz, Hd, s));
+            TRK("train.dropout", CAT_MEM, dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_att, t->dz, Hd, s));
             dz = t->dz;
         }
         if (float* gw = grad_of(gt, pre + "attention.output.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_o, dz, Hd, b.ctx, Hd, gw, s));
-        if (float* gb = grad_of(gt, pre + "attention.output.dense.bias")) MRD_TRY(colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
+        if (float* gb = grad_of(gt, pre + "attention.output.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
         MRD_TRY(run(c, "train.dgrad", dz == t->dz ? p.d_ctx : p.d_ctx0, s));
-        MRD_TRY(attention_backward(b.qkv, b.ctx, t->dctx, c->t_bias, c->t_seq_off, B, S, c->bert_heads,
+        TRK("train.attention_bwd", CAT_ATTN, attention_backward(b.qkv, b.ctx, t->dctx, c->t_bias, c->t_seq_off, B, S, c->bert_heads,
                                    make_drop(seed, site_attn(i), o.p_bert_attn), t->dqkv, s));
         // QKV: one [3*Hd, Hd] product, split into the three parameters (the query block carries the
         // folded 1/sqrt(64): d/dWq = 0.125 * d/dWq')
@@ -810,7 +789,7 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
             MRD_TRY(train_wgrad(c, t, t->w_qkv, t->dqkv, 3 * Hd, b.x, Hd, t->wq_scratch, s));
             const size_t blk = sizeof(float) * static_cast<size_t>(Hd) * Hd;
             if (gq) {
-                MRD_TRY(scale_f32(t->wq_scratch, 1LL * Hd * Hd, 0.125f, s));
+                TRK("train.scale", CAT_MEM, scale_f32(t->wq_scratch, 1LL * Hd * Hd, 0.125f, s));
                 cudaMemcpyAsync(gq, t->wq_scratch, blk, cudaMemcpyDeviceToDevice, s);
             }
             if (gk) cudaMemcpyAsync(gk, t->wq_scratch + 1LL * Hd * Hd, blk, cudaMemcpyDeviceToDevice, s);
@@ -821,20 +800,19 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         float* bv = grad_of(gt, pre + "attention.self.value.bias");
         if (bq || bk || bv) {
             cudaMemsetAsync(t->bq_scratch, 0, sizeof(float) * 3 * Hd, s);
-            MRD_TRY(colsum_bf16(t->dqkv, 3 * Hd, T, 3 * Hd, c->t_nrows, 1.0f, t->bq_scratch, s));
+            TRK("train.colsum", CAT_MEM, colsum_bf16(t->dqkv, 3 * Hd, T, 3 * Hd, c->t_nrows, 1.0f, t->bq_scratch, s));
             if (bq) {
-                MRD_TRY(scale_f32(t->bq_scratch, Hd, 0.125f, s));
+                TRK("train.scale", CAT_MEM, scale_f32(t->bq_scratch, Hd, 0.125f, s));
                 cudaMemcpyAsync(bq, t->bq_scratch, sizeof(float) * Hd, cudaMemcpyDeviceToDevice, s);
             }
             if (bk) cudaMemcpyAsync(bk, t->bq_scratch + Hd, sizeof(float) * Hd, cudaMemcpyDeviceToDevice, s);
             if (bv) cudaMemcpyAsync(bv, t->bq_scratch + 2 * Hd, sizeof(float) * Hd, cudaMemcpyDeviceToDevice, s);
         }
         MRD_TRY(run(c, "train.dgrad", p.d_x, s));    // dx_i = dqkv Wqkv + d_s1
-        c->launches += 12;
     }
     // ---- embeddings: dropout, LayerNorm backward, scatter-add into the three tables
     bf16* dx0 = t->dxa;   // layer 0 wrote dx[0]
-    MRD_TRY(dropout_bf16(dx0, Hd, T, Hd, c->t_nrows, make_drop(seed, SITE_EMB, o.p_bert_hidden), dx0, Hd, s));
+    TRK("train.dropout", CAT_MEM, dropout_bf16(dx0, Hd, T, Hd, c->t_nrows, make_drop(seed, SITE_EMB, o.p_bert_hidden), dx0, Hd, s));
     const std::string em = "text_encoder.encoder.embeddings.";
     float* g_word = grad_of(gt, em + "word_embeddings.weight");
     float* g_pos = grad_of(gt, em + "position_embeddings.weight");
@@ -842,9 +820,8 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
     float* g_lg = grad_of(gt, em + "LayerNorm.weight");
     float* g_lb = grad_of(gt, em + "LayerNorm.bias");
     if (g_word || g_pos || g_type || g_lg || g_lb)
-        MRD_TRY(embed_ln_bwd(t->ids, c->t_row_tok, T, c->t_nrows, S, c->word_emb, c->pos_type, c->emb_g,
+        TRK("train.embed_bwd", CAT_MEM, embed_ln_bwd(t->ids, c->t_row_tok, T, c->t_nrows, S, c->word_emb, c->pos_type, c->emb_g,
                              c->bert_ln_eps, c->vocab, o.pad_idx, dx0, g_word, g_pos, g_type, g_lg, g_lb, s));
-    c->launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "training backward");
     return 0;

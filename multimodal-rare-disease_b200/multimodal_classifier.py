@@ -31,13 +31,17 @@ class _TrainStep(torch.autograd.Function):
     (src/train.py:307-320: backward -> clip_grad_norm_ -> optimizer.step stay the caller's)."""
 
     @staticmethod
-    def forward(ctx, eng, images, input_ids, attention_mask, seed, named_shapes, nc, *params):
-        ctx.eng, ctx.named_shapes = eng, named_shapes
-        return eng.train_forward(images, input_ids, attention_mask, nc, seed)
+    def forward(ctx, eng, images, input_ids, attention_mask, seed, named_shapes, ddp, *params):
+        ctx.eng, ctx.named_shapes, ctx.ddp = eng, named_shapes, ddp
+        return eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
 
     @staticmethod
     def backward(ctx, dlogits):
         grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
+        if ctx.ddp[1]:
+            # data parallel: every gradient of the step lives in one flat buffer -> one all-reduce
+            from .parallel import allreduce_mean_
+            allreduce_mean_(ctx.eng.last_flat_grad, ctx.ddp[2])
         return (None,) * 7 + tuple(grads)
 
 
@@ -188,9 +192,27 @@ class MultimodalClassifier(B200Module):
         named = self._trainable()
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
         shapes = tuple((n, tuple(p.shape)) for n, p in named)
-        logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes, self.num_classes,
-                                  *[p for _, p in named])
+        ddp = self.__dict__.get("_mrd_ddp", (False, None))
+        logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes,
+                                  (self.num_classes, ddp[0], ddp[1]), *[p for _, p in named])
+        if opts["train.bn_train"]:
+            # the library wrote the new running_mean / running_var straight into the BatchNorm buffers
+            # (momentum 0.1, unbiased variance: nn.BatchNorm2d in train mode); the step counters and the
+            # folded eval-mode copies of those statistics are bookkeeping on this side
+            counters = [m.num_batches_tracked for m in self.cnn_encoder.backbone.modules()
+                        if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
+            if counters:
+                torch._foreach_add_(counters, 1)
+            eng._sig = None
         return {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
+
+    def data_parallel(self, enabled: bool = True, process_group=None) -> "MultimodalClassifier":
+        """Training on several GPUs (one process per GPU, replicated parameters, each rank its own
+        batch shard): average the parameter gradients over the ranks inside loss.backward() - a single
+        all-reduce of the step's flat gradient buffer over NCCL.  The caller keeps the ranks' parameters
+        identical at the start (same seed or a broadcast), exactly as with DistributedDataParallel."""
+        self.__dict__["_mrd_ddp"] = (bool(enabled), process_group)
+        return self
 
     def predict(self, images, input_ids, attention_mask) -> Tuple[torch.Tensor, torch.Tensor]:
         self.eval()

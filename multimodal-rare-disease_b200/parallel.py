@@ -94,3 +94,18 @@ class DataParallelForward:
         lo, hi = shard_bounds(total, self.world, self.rank)
         mask = attention_mask[lo:hi] if attention_mask is not None else None
         return self.forward_shard(images[lo:hi], input_ids[lo:hi], mask, total)
+
+
+def allreduce_mean_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Averages a gradient bucket over the data-parallel ranks in place (what DistributedDataParallel
+    does; the reference has no multi-device training).  The B200 training step
+    writes every parameter gradient into ONE flat fp32 buffer (Engine.train_backward), so the whole
+    exchange is a single all-reduce: NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests."""
+    if not dist.is_initialized():
+        return flat
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    return flat

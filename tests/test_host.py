@@ -160,3 +160,33 @@ def test_data_parallel_gather_world2(total):
         assert p.exitcode == 0
     for rank, ok1, ok2, shape in res:
         assert ok1 and ok2 and shape == (total, 10), (rank, ok1, ok2, shape)
+
+
+def _ar_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        views = [flat[:4].view(2, 2), flat[4:]]          # parameter gradients are views of the bucket
+        mrd_b200.allreduce_mean_(flat)
+        want = torch.arange(10, dtype=torch.float32) * 1.5
+        q.put((rank, torch.equal(flat, want), torch.equal(views[0], want[:4].view(2, 2))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_world2():
+    """The training step's only collective: mean of the flat gradient bucket over the ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ar_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res)
+    assert mrd_b200.allreduce_mean_(torch.ones(3)) is not None   # no process group: a no-op

@@ -161,7 +161,7 @@ def test_dropout_mask_statistics(cuda, lib):
 
 
 # --------------------------------------------------------------------------------------- full step
-def _oracle_grads_gpu(sd, images, ids, mask, labels=None, R=None, masks=None, autocast=False):
+def _oracle_grads_gpu(sd, images, ids, mask, labels=None, R=None, masks=None, autocast=False, bn_train=False):
     """Gradients of the (reference-pinned) training oracle, evaluated with torch on the GPU: fp32, or under
     bf16 autocast - the latter is the rounding-noise floor a stock PyTorch bf16 run of the reference has on
     the same case, the yardstick the B200 step is held to."""
@@ -174,7 +174,7 @@ def _oracle_grads_gpu(sd, images, ids, mask, labels=None, R=None, masks=None, au
     torch.set_default_device("cuda")
     try:
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            logits = T.train_forward(work, images.cuda(), ids.cuda(), mask.cuda(), mk)
+            logits = T.train_forward(work, images.cuda(), ids.cuda(), mask.cuda(), mk, bn_train)
         loss = F.cross_entropy(logits.float(), labels.cuda()) if R is None else (logits.float() * R.cuda()).sum()
         loss.backward()
     finally:
@@ -419,13 +419,58 @@ def test_training_loop_follows_reference(cuda):
     assert torch.isfinite(pred).all()
 
 
+def test_train_step_batchnorm_batch_statistics(cuda, sens):
+    """A bare model.train() (what the reference's trainers call, src/train.py:240): the frozen backbone's
+    BatchNorm layers use batch statistics and update their running buffers (TV:143-163 in train mode)."""
+    fix = torch.load(os.path.join(GOLD, "train_p0_bn_train_b4_s32.pt"))
+    model = synth.build_model(0)
+    model.load_state_dict(sens)
+    _zero_dropout(model)
+    model = model.to("cuda:0")
+    model.train()
+    images, ids, mask = synth.make_inputs(fix["B"], fix["S"], fix["seed"], fix["lengths"], H=fix["H"], W=fix["W"])
+    labels = torch.tensor(fix["labels"])
+    out = model(images.cuda(), ids.cuda(), mask.cuda())
+    loss = F.cross_entropy(out["logits"], labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - fix["loss"]) <= 5e-3 * abs(fix["loss"]), (loss.item(), fix["loss"])
+    sd = model.state_dict()
+    rels = {}
+    for k, v in fix["running"].items():
+        got = sd[k].cpu()
+        rels[k] = ((got - v).norm() / (v - sens[k]).norm().clamp_min(1e-12)).item()   # error relative to the UPDATE
+    print("running-stat update rel err:", {k.replace("cnn_encoder.backbone.", ""): round(r, 4) for k, r in rels.items()})
+    for k, r in rels.items():
+        # 4 images of 64x64: layer4 statistics are taken over 16 values per channel after 50 bf16 conv+BN
+        # layers; the stem is exact to bf16 rounding
+        assert r <= (2e-2 if ".bn1.running" in k and "layer" not in k else 1.5e-1), (k, r)
+    assert int(sd["cnn_encoder.backbone.bn1.num_batches_tracked"]) == fix["num_batches_tracked"] == 1
+    assert int(sd["cnn_encoder.backbone.layer4.2.bn3.num_batches_tracked"]) == 1
+    _, g32 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels, bn_train=True)
+    _, g16 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels, bn_train=True, autocast=True)
+    named = dict(model.named_parameters())
+    _compare_with_floor({k: named[k].grad.float().cpu() for k in g32}, g32, g16, "batch-stat BN step")
+    # and against the reference's own sampled gradients for the image branch (the part BN feeds)
+    for k in ("cnn_encoder.projection.0.weight", "cnn_encoder.projection.3.weight", "fusion.fusion_layer.image_proj.weight"):
+        r = fix["grads"][k]
+        err = (_sample(named[k].grad, r["stride"]) - r["sample"]).norm().item() / r["sample"].norm().item()
+        floor = (_sample(g16[k], r["stride"]) - r["sample"]).norm().item() / r["sample"].norm().item()
+        assert err <= 1.3 * floor + GRAD_TOL, (k, err, floor)
+    # eval mode afterwards folds the UPDATED running statistics
+    model.eval()
+    with torch.no_grad():
+        e1 = model(images.cuda(), ids.cuda(), mask.cuda())["logits"]
+    ref_sd = {k: v.float().cpu() for k, v in model.state_dict().items() if v.is_floating_point()}
+    from oracle import forward_oracle
+    want = forward_oracle.multimodal_forward(ref_sd, images, ids, mask)["logits"]
+    assert (e1.cpu() - want).abs().max().item() <= 2e-2
+
+
 def test_train_mode_refuses_what_it_cannot_do(cuda):
     model = synth.build_model(0).to("cuda:0")
-    model.train()          # BatchNorm in train mode: batch statistics are not on this path yet
+    model.train()
     images, ids, mask = synth.make_inputs(2, 16, 1, None, H=32, W=32)
-    with pytest.raises(Exception, match="BatchNorm|backbone"):
-        model(images.cuda(), ids.cuda(), mask.cuda())
-    model.cnn_encoder.backbone.eval()
     model.cnn_encoder.backbone.layer4.requires_grad_(True)
     with pytest.raises(NotImplementedError, match="backbone"):
         model(images.cuda(), ids.cuda(), mask.cuda())
