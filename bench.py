@@ -186,7 +186,8 @@ def main():
     ap.add_argument("--global-batch", type=int, default=4096)
     ap.add_argument("--img-chunk", type=int, default=0)
     ap.add_argument("--tok-chunk", type=int, default=0)
-    ap.add_argument("--cpu-samples", type=int, default=32)
+    ap.add_argument("--cpu-samples", type=int, default=128,
+                    help="samples per CPU pass: the reference arm's step, and (x2) the cpu_baseline leg")
     ap.add_argument("--micro-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -350,9 +351,10 @@ def main():
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, threads = cpu_forward_timer(args.cpu_samples, 3, 1)
+        n_cpu = 2 * args.cpu_samples   # ~6 s per pass on 16 cores: 1 warm-up + 2 timed passes = ~20 s of CPU work
+        v, sec, cores, threads = cpu_forward_timer(n_cpu, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_samples} samples of the same workload, 1 warm-up + 3 timed passes, "
+               "sample": f"{n_cpu} samples of the same workload, 1 warm-up + 2 timed passes, "
                          f"{sec:.2f} s per pass (oracle/forward_oracle.py, fp32, {threads} threads of {cores} host cores)"}
 
     if rank == 0:

@@ -148,6 +148,10 @@ struct mrd_ctx {
     long long cnn_ws_epoch = 0;    // same for the ResNet workspace
     long long text_run_epoch = 0;  // bumped by every eval-mode BERT pass (overwrites the packing tables)
     bool fp32_check = false;
+    // load_weights synchronises the device before re-packing and the stream afterwards (safe for callers
+    // that use several streams or free their tensors right away); "load_sync" = 0 drops both when the
+    // caller keeps its tensors alive and works on one stream (the training loop: no host stall per step)
+    bool load_sync = true;
     RawTable raw;
     Fp32Arena f32_ws;
     Fp32Opts f32_opts() const {
@@ -1197,6 +1201,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fusion_residual") { c->fusion_residual = v != 0.0; c->batch_plans.clear(); }
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
+    else if (k == "load_sync") c->load_sync = v != 0.0;
     else if (k.rfind("train.", 0) == 0) return train_set_option(c, k, v);
     else {
         set_last_error("mrd_ctx_set_option: unknown option '%s'", k.c_str());
@@ -1228,7 +1233,7 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
         any_head |= nm.rfind("classifier.", 0) == 0;
     }
     // weights are rewritten in place: nothing may still be reading them
-    cudaError_t e = cudaDeviceSynchronize();
+    cudaError_t e = c->load_sync ? cudaDeviceSynchronize() : cudaSuccess;
     if (e != cudaSuccess) return cuda_fail(e, "mrd_ctx_load_weights: device sync");
     const size_t n_blocks = c->blocks.size(), n_layers = c->layers.size(), n_head = c->head_hidden.size();
     if (c->train) train_invalidate_packs(c);
@@ -1242,7 +1247,7 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
         c->text_plans.clear();
         c->batch_plans.clear();
     }
-    e = cudaStreamSynchronize(s);  // the caller may free or mutate its fp32 tensors after return
+    e = c->load_sync ? cudaStreamSynchronize(s) : cudaSuccess;  // the caller may free or mutate its fp32 tensors after return
     if (e != cudaSuccess) return cuda_fail(e, "mrd_ctx_load_weights: packing kernels");
     return 0;
 }

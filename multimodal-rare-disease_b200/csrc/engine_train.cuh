@@ -253,13 +253,13 @@ int train_ensure_plan(mrd_ctx* c, int B, int S) {
         GemmLaunch* all[] = {&p.qkv, &p.o, &p.f1, &p.f2, &p.d_g, &p.d_h1, &p.d_ctx, &p.d_x, &p.d_g0, &p.d_ctx0};
         for (GemmLaunch* g : all) g->p.dyn_rows = c->t_nrows;
     }
-    // dW[out,in] = dY^T[out,Tp] * (X^T[in,Tp])^T ; fp32 result, destination patched per launch
+    // dW[out,in] += dY^T[out,Tp] * (X^T[in,Tp])^T : split-K over the live tokens, fp32 partial sums added
+    // into the (zeroed) destination, which is patched per launch
     const int K = static_cast<int>(Tp);
-    MRD_TRY(plan_gemm(&t->w_f2, t->At, Tp, Hd, K, t->Bt, F, nullptr, nullptr, 0, nullptr, 0, t->wq_scratch, F, ACT_NONE));
-    MRD_TRY(plan_gemm(&t->w_f1, t->At, Tp, F, K, t->Bt, Hd, nullptr, nullptr, 0, nullptr, 0, t->wq_scratch, Hd, ACT_NONE));
-    MRD_TRY(plan_gemm(&t->w_o, t->At, Tp, Hd, K, t->Bt, Hd, nullptr, nullptr, 0, nullptr, 0, t->wq_scratch, Hd, ACT_NONE));
-    MRD_TRY(plan_gemm(&t->w_qkv, t->At, Tp, 3 * Hd, K, t->Bt, Hd, nullptr, nullptr, 0, nullptr, 0, t->wq_scratch, Hd,
-                      ACT_NONE));
+    MRD_TRY(plan_gemm_splitk(&t->w_f2, t->At, Tp, Hd, K, t->Bt, F, t->wq_scratch, F, c->t_nrows));
+    MRD_TRY(plan_gemm_splitk(&t->w_f1, t->At, Tp, F, K, t->Bt, Hd, t->wq_scratch, Hd, c->t_nrows));
+    MRD_TRY(plan_gemm_splitk(&t->w_o, t->At, Tp, Hd, K, t->Bt, Hd, t->wq_scratch, Hd, c->t_nrows));
+    MRD_TRY(plan_gemm_splitk(&t->w_qkv, t->At, Tp, 3 * Hd, K, t->Bt, Hd, t->wq_scratch, Hd, c->t_nrows));
     t->B = B; t->S = S; t->Ta = T; t->Tp = K;
     t->text_ws_epoch = c->text_ws_epoch;
     return 0;
@@ -564,9 +564,9 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         MRD_TRY(run_backbone_train(c, images, img_dtype, B, H, W, t->pooled, s));
     else
         MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, nullptr, s));
-    MRD_TRY(lin_fwd(c, "cnn_encoder.projection.0", t->pooled, c->feat_dim, B, t->a1, c->proj1.out, MRD_ACT_RELU,
+    MRD_TRY(lin_fwd(c, "cnn_encoder.projection.0", t->pooled, c->feat_dim, B, t->a1, c->proj1.out, MRD_ACT_NONE,
                     nullptr, 0, s));
-    TRK("train.dropout", CAT_MEM, dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));
+    TRK("train.dropout", CAT_MEM, relu_dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));
     MRD_TRY(lin_fwd(c, "cnn_encoder.projection.3", t->p1, c->proj1.out, B, t->img, c->proj2.out, MRD_ACT_NONE,
                     nullptr, 0, s));
 
@@ -614,8 +614,8 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
                     c->fusion_residual ? t->tp : nullptr, Fd, s));
     TRK("train.ln_f32", CAT_MEM, ln_fwd_f32(t->pre_i, Fd, c->ln_i_g, c->ln_i_b, c->fusion_ln_eps, B, Fd, t->cat, 2 * Fd, s));
     TRK("train.ln_f32", CAT_MEM, ln_fwd_f32(t->pre_t, Fd, c->ln_t_g, c->ln_t_b, c->fusion_ln_eps, B, Fd, t->cat + Fd, 2 * Fd, s));
-    MRD_TRY(lin_fwd(c, f + "fusion.0", t->cat, 2 * Fd, B, t->g0, Fd, MRD_ACT_RELU, nullptr, 0, s));
-    TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->fh, s));
+    MRD_TRY(lin_fwd(c, f + "fusion.0", t->cat, 2 * Fd, B, t->g0, Fd, MRD_ACT_NONE, nullptr, 0, s));
+    TRK("train.dropout", CAT_MEM, relu_dropout_f32(t->g0, B, Fd, make_drop(seed, SITE_FUSION_MLP, o.p_fusion), t->fh, s));
     MRD_TRY(lin_fwd(c, f + "fusion.3", t->fh, Fd, B, t->fused, Fd, MRD_ACT_NONE, nullptr, 0, s));
 
     // ---- head (src/multimodal_classifier.py:73-83)
@@ -625,8 +625,8 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         char nm[64];
         snprintf(nm, sizeof(nm), "classifier.classifier.%zu", 3 * j);
         const int n = c->head_hidden[j].out;
-        MRD_TRY(lin_fwd(c, nm, x, ld, B, t->g0, n, MRD_ACT_RELU, nullptr, 0, s));
-        TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(j), o.p_head), t->hh[j], s));
+        MRD_TRY(lin_fwd(c, nm, x, ld, B, t->g0, n, MRD_ACT_NONE, nullptr, 0, s));
+        TRK("train.dropout", CAT_MEM, relu_dropout_f32(t->g0, B, n, make_drop(seed, SITE_HEAD + static_cast<unsigned>(j), o.p_head), t->hh[j], s));
         x = t->hh[j];
         ld = n;
     }
@@ -643,8 +643,8 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
 // dW = dY^T X through the tcgen05 GEMM: stage both operands token-minor, fp32 result into `dst`.
 int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* dY, int n_out, const bf16* X, int n_in,
                 float* dst, cudaStream_t s) {
-    TRK("train.transpose", CAT_MEM, transpose_pad_bf16(dY, n_out, t->Ta, n_out, c->t_nrows, t->At, t->Tp, s));
-    TRK("train.transpose", CAT_MEM, transpose_pad_bf16(X, n_in, t->Ta, n_in, c->t_nrows, t->Bt, t->Tp, s));
+    TRK("train.transpose", CAT_MEM, transpose_pad2_bf16(dY, n_out, n_out, t->At, X, n_in, n_in, t->Bt, t->Ta, c->t_nrows,
+                                                        t->Tp, s));
     return run_f32(c, "train.wgrad", plan, dst, n_in, s);
 }
 
@@ -786,6 +786,7 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         float* gk = grad_of(gt, pre + "attention.self.key.weight");
         float* gv = grad_of(gt, pre + "attention.self.value.weight");
         if (gq || gk || gv) {
+            cudaMemsetAsync(t->wq_scratch, 0, sizeof(float) * 3 * static_cast<size_t>(Hd) * Hd, s);
             MRD_TRY(train_wgrad(c, t, t->w_qkv, t->dqkv, 3 * Hd, b.x, Hd, t->wq_scratch, s));
             const size_t blk = sizeof(float) * static_cast<size_t>(Hd) * Hd;
             if (gq) {

@@ -227,6 +227,7 @@ int linear(const RawTable& t, const std::string& name, const float* x, long long
     g.bias = b->p;
     g.act = act;
     g.res = res; g.ldr = ldr;
+    g.ksplit = 1;   // check mode: one CTA owns each output element (bit-reproducible, no atomics)
     return simt_gemm(g, s);
 }
 

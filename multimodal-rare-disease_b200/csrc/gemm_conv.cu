@@ -152,7 +152,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     constexpr int NSUB = BLOCK_N / 64;
-    const int num_k = p.num_taps * p.kc_per_tap;
+    int num_k = p.num_taps * p.kc_per_tap;
+    if (p.dyn_k) {   // token-packed contraction (weight gradients): only the live K blocks
+        int live_k = (__ldg(p.dyn_k) + C::BLOCK_K - 1) / C::BLOCK_K;
+        live_k = live_k < 1 ? 1 : live_k;
+        num_k = live_k < num_k ? live_k : num_k;
+    }
     const int box_rows = p.tw * p.th * p.nb;
     const uint32_t a_box_bytes = static_cast<uint32_t>(box_rows) * C::ROW_BYTES;
     const uint32_t stage_tx = a_box_bytes + C::B_STAGE;
@@ -163,7 +168,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int live = (__ldg(p.dyn_rows) + kBlockM - 1) / kBlockM * p.n_tiles_n;
         total_tiles = live < total_tiles ? live : total_tiles;
     }
-    const int my_tiles = total_tiles > bid ? (total_tiles - bid + nblk - 1) / nblk : 0;
+    // split-K: work item = (output tile, K slice); item i covers tile i % total_tiles, slice i / total_tiles.
+    // ksplit == 1 (every launch of the forward) makes items and tiles the same thing.
+    int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+    ksplit = ksplit < num_k ? ksplit : num_k;
+    const int total_items = total_tiles * ksplit;
+    const int my_tiles = total_items > bid ? (total_items - bid + nblk - 1) / nblk : 0;
 
     if (warp == 0 && WRES) {
         // ------------------------------------------------------------ TMA producer, weights-resident modes
@@ -291,9 +301,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = bid; tile < total_tiles; tile += nblk) {
-            const TileCoord t = decode_tile(p, tile);
-            for (int ks = 0; ks < num_k; ++ks) {
+        for (int item = bid; item < total_items; item += nblk) {
+            const int split = item / total_tiles;
+            const TileCoord t = decode_tile(p, item - split * total_tiles);
+            const int k_begin = split * num_k / ksplit, k_end = (split + 1) * num_k / ksplit;
+            for (int ks = k_begin; ks < k_end; ++ks) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
@@ -317,13 +329,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = bid; tile < total_tiles; tile += nblk, ++it) {
+        for (int item = bid; item < total_items; item += nblk, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            for (int ks = 0; ks < num_k; ++ks) {
+            const int split = item / total_tiles;
+            const int k_begin = split * num_k / ksplit, k_end = (split + 1) * num_k / ksplit;
+            for (int ks = k_begin; ks < k_end; ++ks) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -335,10 +349,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     for (int k = 0; k < C::BLOCK_K / 16; ++k) {
                         // +32 bytes (encoded >>4) per 16-element K slice inside the swizzle span
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                  (ks | k) != 0 ? 1u : 0u);
+                                  (ks != k_begin || k != 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));
-                    if (ks == num_k - 1) umma_commit(tfull_bar(acc));
+                    if (ks == k_end - 1) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -353,7 +367,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             int slot = 0;
             uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                const TileCoord t = decode_tile(p, bid + it * nblk);
+                const TileCoord t = decode_tile(p, (bid + it * nblk) % total_tiles);
                 for (int sub = 0; sub < NSUB; ++sub) {
                     mbar_wait(rempty_bar(slot), phase ^ 1u);
                     if (lane == 0) {
@@ -380,13 +394,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int rslot = 0;
         uint32_t rphase = 0;
 
-        TileCoord t = decode_tile(p, bid);
+        TileCoord t = decode_tile(p, total_tiles > 0 ? bid % total_tiles : 0);
         for (int q = 0; q < nq; ++q) {
             const int sub = q % NSUB;
             const int it = q / NSUB;
             const int acc = it & 1;
             const uint32_t buf = q & 1u;
-            if (sub == 0) t = decode_tile(p, bid + it * nblk);
+            if (sub == 0) t = decode_tile(p, (bid + it * nblk) % total_tiles);
             const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;  // first global column of this thread
 
             if (sub == 0) {
@@ -446,10 +460,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     const long long pix =
                         (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
                     float* f32_row = p.out_f32 + pix * p.ld_f32 + col0;
+                    if (p.f32_accum) {   // split-K partial result: reduce in L2
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(f32_row + j) =
-                            make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            atomicAdd(reinterpret_cast<float4*>(f32_row + j),
+                                      make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(f32_row + j) =
+                                make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
                 }
             }
             // staging buffer `buf` was the source of TMA store q-2: it must have been read out
@@ -551,6 +572,12 @@ void pick_pipeline(ConvGemmParams* p, int block_n, bool stem) {
     p->stages = s;
     p->ring = r;
 }
+
+#define MRD_GEMM_TRY(expr)          \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__ != 0) return rc__; \
+    } while (0)
 
 int pick_block_n(int n, long long m_tiles, int sms) {
     // widest N tile that divides N and still gives every SM at least one tile
@@ -675,6 +702,37 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
         p.r_map = p.a_map[0];  // never dereferenced (has_res == 0)
     }
     return finish_plan(g, bn);
+}
+
+int plan_gemm_splitk(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
+                     const __nv_bfloat16* W, int N, float* out_f32, long long ld_f32, const int* dyn_k) {
+    if (!out_f32) {
+        set_last_error("plan_gemm_splitk: an fp32 destination is required");
+        return -1;
+    }
+    MRD_GEMM_TRY(plan_gemm(g, A, lda, M, K, W, N, nullptr, nullptr, 0, nullptr, 0, out_f32, ld_f32, ACT_NONE));
+    // plan_gemm sized the N tile for a single pass (64 wide when there are few tiles); with split-K the SMs
+    // are filled by K slices instead, so take the widest tile (best operand reuse) and rebuild the B map
+    const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = encode_tensor_map(&g->p.b_map, W, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    MRD_GEMM_TRY(finish_plan(g, bn));
+    const int sms = gemm_num_sms();
+    int ks = sms / g->p.total_tiles;
+    const int num_k = K / 64;
+    if (ks > num_k / 4) ks = num_k / 4;   // at least 4 K blocks per work item
+    if (ks < 1) ks = 1;
+    g->p.ksplit = ks;
+    g->p.f32_accum = 1;
+    g->p.dyn_k = dyn_k;
+    const long long items = static_cast<long long>(g->p.total_tiles) * ks;
+    g->grid = items < sms ? static_cast<int>(items) : sms;
+    return 0;
 }
 
 int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Cin,

@@ -46,6 +46,13 @@ struct alignas(64) ConvGemmParams {
     int total_tiles;
     int act;
     int store_bf16;                      // 1: write bf16 output through c_map
+    // split-K (generic mode only; weight gradients dW = dY^T X contract over the tokens, few output tiles):
+    // the K loop of every output tile is cut into `ksplit` work items whose fp32 results are ADDED into
+    // out_f32 (f32_accum = 1; the destination must be zeroed by the caller).  dyn_k (device, optional):
+    // live contraction length in elements (token-packed operands), rounded up to 64 inside the kernel.
+    int ksplit;
+    int f32_accum;
+    const int* dyn_k;
 };
 
 struct GemmLaunch {
@@ -87,6 +94,12 @@ int plan_conv3x3_flat(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, 
 // Wst: [64][7][32] bf16 (tap row r, then 8 pixels x 4 channels; BN folded), Y: [N,H/2,W/2,64].
 int plan_stem(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W,
               const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* Y, int act);
+
+// Weight-gradient GEMM: out_f32[M,N] += A[M,K] * W[N,K]^T with fp32 accumulation across split-K work
+// items (wide 128x256 tiles for operand reuse, K cut so that every SM gets a work item).  out_f32 must be
+// zero before the launch.  dyn_k: optional device int, the live part of K (<= K).
+int plan_gemm_splitk(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K,
+                     const __nv_bfloat16* W, int N, float* out_f32, long long ld_f32, const int* dyn_k);
 
 int launch_gemm(const GemmLaunch* g, cudaStream_t stream);
 

@@ -14,11 +14,6 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 
-struct ConvArgs {
-    SimtConv cv;
-    int on;
-};
-
 __device__ __forceinline__ float ld_elem(const void* p, long long i, int is_bf16) {
     return is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i])
                    : __ldg(static_cast<const float*>(p) + i);
@@ -54,7 +49,13 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemm p, SimtConv cv)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    int k_lo = 0;
+    if (!CONV && gridDim.z > 1) {   // split-K: this CTA's slice of the contraction
+        const int per = ((K + static_cast<int>(gridDim.z) - 1) / static_cast<int>(gridDim.z) + BK - 1) / BK * BK;
+        k_lo = static_cast<int>(blockIdx.z) * per;
+        K = min(K, k_lo + per);
+    }
+    for (int k0 = k_lo; k0 < K; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int e = tid + i * 256;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemm p, SimtConv cv)
             const int n = n0 + tn * 4 + j;
             if (n >= p.N) continue;
             float v = acc[i][j] * p.alpha;
-            if (p.bias) v += __ldg(p.bias + n);
+            if (p.bias && gridDim.z == 1) v += __ldg(p.bias + n);
             if (CONV) {
                 v = (v - __ldg(cv.mean + n)) / sqrtf(__ldg(cv.var + n) + cv.eps) * __ldg(cv.gamma + n) +
                     __ldg(cv.beta + n);
@@ -121,6 +122,13 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtGemm p, SimtConv cv)
                 const long long o = (static_cast<long long>(img) * p.N + n) * HoWo + hw;
                 if (cv.residual) v += __ldg(cv.residual + o);
                 p.C[o] = apply_act(v, p.act);
+            } else if (gridDim.z > 1) {
+                float v2 = acc[i][j] * p.alpha;
+                if (blockIdx.z == 0) {
+                    if (p.bias) v2 += __ldg(p.bias + n);
+                    if (p.res) v2 += __ldg(p.res + m * p.ldr + n);
+                }
+                atomicAdd(p.C + m * p.ldc + n, v2);
             } else {
                 v = apply_act(v, p.act);
                 if (p.res) v += __ldg(p.res + m * p.ldr + n);
@@ -152,6 +160,26 @@ int simt_gemm(const SimtGemm& g, cudaStream_t s) {
         return -1;
     }
     dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
+    int ks = g.ksplit;
+    const bool can_split = g.C && !g.C16 && g.act == MRD_ACT_NONE && !g.dyn_k && !g.dyn_m &&
+                           (g.accumulate || g.ldc == g.N);
+    if (ks == 0 && can_split) {
+        const long long tiles = static_cast<long long>(grid.x) * grid.y;
+        if (tiles < 96 && g.K >= 256) {
+            ks = static_cast<int>(148 / tiles);
+            if (ks > g.K / 128) ks = g.K / 128;
+        }
+    }
+    if (ks > 1 && can_split) {
+        if (!g.accumulate) {
+            cudaError_t e = cudaMemsetAsync(g.C, 0, sizeof(float) * static_cast<size_t>(g.M) * g.N, s);
+            if (e != cudaSuccess) {
+                set_last_error("simt_gemm: cudaMemsetAsync: %s", cudaGetErrorString(e));
+                return -static_cast<int>(e);
+            }
+        }
+        grid.z = ks;
+    }
     SimtConv none{};
     simt_gemm_kernel<false><<<grid, 256, 0, s>>>(g, none);
     return check_launch("simt_gemm");

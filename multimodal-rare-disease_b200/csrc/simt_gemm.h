@@ -41,6 +41,10 @@ struct SimtGemm {
     int act = 0;               // MRD_ACT_*
     int accumulate = 0;        // C += result (fp32 output only)
     int M = 0, N = 0, K = 0;
+    int ksplit = 0;            // 0: automatic.  > 1: the K loop is cut into slices (grid.z) whose partial sums are
+                               // added atomically into C (fp32 only, no activation; bias / residual come from
+                               // slice 0); C is zeroed first unless `accumulate` is set.  Skinny problems
+                               // (rows = batch size) otherwise run a long serial K loop on a handful of CTAs.
     const int* dyn_k = nullptr;    // optional device int: contraction length min(K, *dyn_k)
     const int* dyn_m = nullptr;    // optional device int: rows min(M, *dyn_m)
 };

@@ -74,6 +74,12 @@ __global__ void dropout_f32_kernel(const float* __restrict__ x, long long n, Dro
     y[i] = drop_keep(d, static_cast<unsigned long long>(i)) ? x[i] * d.scale : 0.0f;
 }
 
+__global__ void relu_dropout_f32_kernel(const float* __restrict__ x, long long n, DropCfg d, float* __restrict__ y) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = drop_keep(d, static_cast<unsigned long long>(i)) ? fmaxf(x[i], 0.0f) * d.scale : 0.0f;
+}
+
 __global__ void head_dropout_f32_kernel(const float* __restrict__ x, int rows, int heads, int hd, DropCfg d,
                                         float* __restrict__ y, float* __restrict__ w_out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -304,22 +310,48 @@ __global__ void gelu_kernel(const bf16* __restrict__ u, const bf16* __restrict__
 }
 
 // ------------------------------------------------------------------ transposes / reductions
-// 64 rows x 64 columns per block through shared memory; reads and writes are 128-byte row segments.
+// 64 rows x 64 columns per block.  Works on 32-bit words (bf16 pairs): a thread reads the same word of two
+// adjacent rows, re-pairs them ([x(r,c) x(r,c+1)], [x(r+1,c) x(r+1,c+1)] -> [x(r,c) x(r+1,c)], [x(r,c+1)
+// x(r+1,c+1)]) and the block transposes the words through a padded shared tile: every global access is a
+// 128-byte warp row, every shared access conflict-free or 2-way.  blockIdx.z selects one of two operands
+// so the dY^T and X^T of a weight gradient are staged by one launch.
+struct TransposeJob {
+    const bf16* x;
+    long long ldx;
+    int width;
+    bf16* y;
+};
+
 __global__ void __launch_bounds__(256)
-transpose_pad_kernel(const bf16* __restrict__ x, long long ldx, int rows, int width,
-                     const int* __restrict__ dyn_rows, bf16* __restrict__ y, int Kp) {
-    __shared__ bf16 tile[64][66];
+transpose_pad_kernel(TransposeJob j0, TransposeJob j1, int rows, const int* __restrict__ dyn_rows, int Kp) {
+    __shared__ uint32_t tile[64][33];
+    const TransposeJob job = blockIdx.z ? j1 : j0;
     if (dyn_rows) rows = min(rows, __ldg(dyn_rows));
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-    for (int i = ty; i < 64; i += 4) {
-        const int r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < rows && c < width) ? x[r * ldx + c] : __float2bfloat16(0.0f);
+    if (c0 >= job.width) return;
+    // the consumer (split-K GEMM with dyn_k) reads K blocks below round_up(live, 64) only
+    if (dyn_rows && r0 >= ((rows + 63) & ~63)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = c0 + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rp = warp * 4 + i;          // row pair 0..31
+        const int r = r0 + 2 * rp;
+        uint32_t a = 0u, b = 0u;
+        if (c < job.width) {
+            if (r < rows) a = *reinterpret_cast<const uint32_t*>(job.x + r * job.ldx + c);
+            if (r + 1 < rows) b = *reinterpret_cast<const uint32_t*>(job.x + (r + 1) * job.ldx + c);
+        }
+        tile[2 * lane][rp] = (a & 0xffffu) | (b << 16);
+        tile[2 * lane + 1][rp] = (a >> 16) | (b & 0xffff0000u);
     }
     __syncthreads();
-    for (int i = ty; i < 64; i += 4) {
-        const int c = c0 + i, r = r0 + tx;
-        if (c < width && r < Kp) y[static_cast<long long>(c) * Kp + r] = tile[tx][i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int cc = warp * 8 + i;          // output row (= input column) within the tile
+        const int r = r0 + 2 * lane;
+        if (c0 + cc < job.width && r < Kp)
+            *reinterpret_cast<uint32_t*>(job.y + static_cast<long long>(c0 + cc) * Kp + r) = tile[cc][lane];
     }
 }
 
@@ -399,8 +431,16 @@ embed_ln_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ r
                     float* __restrict__ dpos, float* __restrict__ dtype0, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
     constexpr int WIDTH = 768, NCH = 3;
+    __shared__ float red[8][WIDTH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (dyn_rows) rows = min(rows, __ldg(dyn_rows));
+    // column sums that every row feeds (LayerNorm weight / bias, token_type row 0): registers, one block
+    // reduction and one atomic per column and block at the end
+    float ag[NCH][8], ab[NCH][8], at[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = at[c][j] = 0.0f;
     for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows;
          row += static_cast<long long>(gridDim.x) * 8) {
         const long long tok = row_tok ? __ldg(row_tok + row) : row;
@@ -440,8 +480,8 @@ embed_ln_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ r
             for (int j = 0; j < 8; ++j) {
                 const float xh = x[c][j] * rstd;
                 x[c][j] = xh;
-                if (dgamma) atomicAdd(dgamma + col + j, g[c][j] * xh);
-                if (dbeta) atomicAdd(dbeta + col + j, g[c][j]);
+                ag[c][j] += g[c][j] * xh;
+                ab[c][j] += g[c][j];
                 const float gg = g[c][j] * __ldg(gamma + col + j);
                 g[c][j] = gg;
                 m1 += gg;
@@ -456,10 +496,27 @@ embed_ln_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ r
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float d = rstd * (g[c][j] - m1 - x[c][j] * m2);
+                at[c][j] += d;
                 if (dword && live_word) atomicAdd(dword + id * WIDTH + col + j, d);
                 if (dpos) atomicAdd(dpos + static_cast<long long>(pos) * WIDTH + col + j, d);
-                if (dtype0) atomicAdd(dtype0 + col + j, d);
             }
+        }
+    }
+    for (int pass = 0; pass < 3; ++pass) {
+        float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dtype0);
+        if (!dst) continue;  // uniform
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                red[warp][(c * 32 + lane) * 8 + j] = pass == 0 ? ag[c][j] : (pass == 1 ? ab[c][j] : at[c][j]);
+        __syncthreads();
+        for (int col = threadIdx.x; col < WIDTH; col += 256) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][col];
+            atomicAdd(dst + col, t);
         }
     }
 }
@@ -572,6 +629,12 @@ int dropout_f32(const float* x, int rows, int width, DropCfg d, float* y, cudaSt
     dropout_f32_kernel<<<nblk(n, 256), 256, 0, s>>>(x, n, d, y);
     return check_launch("dropout_f32");
 }
+int relu_dropout_f32(const float* x, int rows, int width, DropCfg d, float* y, cudaStream_t s) {
+    const long long n = static_cast<long long>(rows) * width;
+    if (n <= 0) return 0;
+    relu_dropout_f32_kernel<<<nblk(n, 256), 256, 0, s>>>(x, n, d, y);
+    return check_launch("relu_dropout_f32");
+}
 int head_dropout_f32(const float* x, int rows, int heads, int head_dim, DropCfg d, float* y, float* w_out,
                      cudaStream_t s) {
     const long long n = static_cast<long long>(rows) * heads * head_dim;
@@ -654,9 +717,19 @@ int gelu_bwd_bf16(const bf16* u, const bf16* dg, int rows, int width, const int*
 
 int transpose_pad_bf16(const bf16* x, long long ldx, int rows, int width, const int* dyn_rows, bf16* y, int Kp,
                        cudaStream_t s) {
-    if (Kp <= 0 || width <= 0) return 0;
-    dim3 grid((Kp + 63) / 64, (width + 63) / 64);
-    transpose_pad_kernel<<<grid, 256, 0, s>>>(x, ldx, rows, width, dyn_rows, y, Kp);
+    return transpose_pad2_bf16(x, ldx, width, y, nullptr, 0, 0, nullptr, rows, dyn_rows, Kp, s);
+}
+int transpose_pad2_bf16(const bf16* x0, long long ldx0, int width0, bf16* y0, const bf16* x1, long long ldx1,
+                        int width1, bf16* y1, int rows, const int* dyn_rows, int Kp, cudaStream_t s) {
+    if (Kp <= 0 || width0 <= 0) return 0;
+    if (Kp % 2 || width0 % 2 || width1 % 2 || ldx0 % 2 || ldx1 % 2) {
+        set_last_error("transpose_pad_bf16: odd extent");
+        return -1;
+    }
+    const int wmax = width0 > width1 ? width0 : width1;
+    dim3 grid((Kp + 63) / 64, (wmax + 63) / 64, x1 ? 2 : 1);
+    TransposeJob j0{x0, ldx0, width0, y0}, j1{x1, ldx1, width1, y1};
+    transpose_pad_kernel<<<grid, 256, 0, s>>>(j0, j1, rows, dyn_rows, Kp);
     return check_launch("transpose_pad_bf16");
 }
 int colsum_bf16(const bf16* x, long long ldx, int rows, int width, const int* dyn_rows, float scale, float* out,
@@ -709,7 +782,7 @@ int embed_ln_bwd(const long long* ids, const int* row_tok, int rows, const int* 
                  float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta, cudaStream_t s) {
     if (rows <= 0) return 0;
     unsigned grid = nblk(rows, 8);
-    if (grid > 148u * 4u) grid = 148u * 4u;
+    if (grid > 148u) grid = 148u;
     embed_ln_bwd_kernel<<<grid, 256, 0, s>>>(ids, row_tok, rows, dyn_rows, S, word, pos_type, gamma, eps, vocab,
                                              pad_idx, dy, dword, dpos, dtype0, dgamma, dbeta);
     return check_launch("embed_ln_bwd");

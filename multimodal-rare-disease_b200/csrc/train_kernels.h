@@ -17,6 +17,8 @@ namespace mrd {
 int dropout_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
                  DropCfg d, __nv_bfloat16* y, long long ldy, cudaStream_t s);
 int dropout_f32(const float* x, int rows, int width, DropCfg d, float* y, cudaStream_t s);
+// y = dropout(relu(x)): Linear -> ReLU -> Dropout of the projection / fusion MLP / head, on the GEMM's output
+int relu_dropout_f32(const float* x, int rows, int width, DropCfg d, float* y, cudaStream_t s);
 // Dropout of the length-1 cross-attention weights (src/fusion_model.py:164-165): the softmax over one
 // key is 1, so after dropout head h of row r carries weight w = keep(r*heads + h) ? scale : 0 and
 // y[r, h*hd + j] = w * x[r, h*hd + j].  w_out (optional): [rows, heads].  Its own backward as well.
@@ -56,6 +58,10 @@ int gelu_bwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* dg, int rows, int
 // row count are zero-filled so stale rows of the token-packed buffers contribute nothing.
 int transpose_pad_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
                        __nv_bfloat16* y, int Kp, cudaStream_t s);
+// two operands (same rows / Kp) in one launch
+int transpose_pad2_bf16(const __nv_bfloat16* x0, long long ldx0, int width0, __nv_bfloat16* y0,
+                        const __nv_bfloat16* x1, long long ldx1, int width1, __nv_bfloat16* y1, int rows,
+                        const int* dyn_rows, int Kp, cudaStream_t s);
 // out[c] += scale * sum_r x[r,c]   (bias gradients)
 int colsum_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
                 float scale, float* out, cudaStream_t s);

@@ -188,6 +188,9 @@ class MultimodalClassifier(B200Module):
         if self.__dict__.get("_mrd_train_opts") != opts:
             for k, v in opts.items():
                 eng.set_option(k, v)
+            # the optimizer rewrites the parameters every step: re-pack them in stream order instead of
+            # stalling the host on a device synchronisation per step (the engine keeps the tensors alive)
+            eng.set_option("load_sync", 0.0)
             self.__dict__["_mrd_train_opts"] = opts
         named = self._trainable()
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
