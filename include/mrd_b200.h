@@ -210,7 +210,7 @@ int mrd_mask_to_bias(const void* mask, int mask_dtype, int B, int S, float* bias
  * "train.p_fusion" 0.3, "train.p_head" 0.5, "train.pad_idx" 0; masks are a pure function of `seed`).
  * Keeps the activations the backward needs inside the context; one forward may be pending at a time.
  * The ResNet50 backbone must be frozen (the reference default, src/config.py:64) and is run forward
- * only.  S <= 128, B <= one pass.  logits: f32 [B,C]. */
+ * only.  S <= 512, B <= one pass.  logits: f32 [B,C]. */
 int mrd_train_forward(mrd_ctx* ctx, const void* images, int img_dtype, const long long* ids,
                       const void* mask, int mask_dtype, int B, int H, int W, int S,
                       unsigned long long seed, float* logits, void* stream);
@@ -230,17 +230,20 @@ int mrd_dropout_mask(unsigned long long seed, unsigned int site, double p, long 
                      void* stream);
 
 /* mrd_attention_bf16 with dropout on the probabilities (train mode); element index of (b,h,q,k) is
- * ((b*heads + h)*S + q)*S + k.  S <= 128. */
+ * ((b*heads + h)*S + q)*S + k. */
 int mrd_attention_train_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads,
                              unsigned long long seed, unsigned int site, double p, void* out,
                              void* stream);
 
 /* Backward of the fused attention: qkv / dqkv bf16 [rows, 3*heads*64], ctx (forward output) / dctx bf16
  * [rows, heads*64]; dQ is the gradient of the pre-scaled Q.  seq_off as mrd_attention_varlen_bf16 or
- * NULL for the dense layout.  S <= 128 (one 128x128 tile per (sample, head)). */
+ * NULL for the dense layout.  S <= 128: one 128x128 tile per (sample, head), dkv_acc may be NULL.
+ * 128 < S <= 512: tiled over 128x128 blocks; dkv_acc = ZEROED f32 scratch [rows, 2*heads*64] (dK | dV are
+ * accumulated there across query blocks and then converted into dqkv), rows = row count of the tensors. */
 int mrd_attention_bwd_bf16(const void* qkv, const void* ctx, const void* dctx, const float* mask_bias,
                            const int* seq_off, int B, int S, int heads, unsigned long long seed,
-                           unsigned int site, double p, void* dqkv, void* stream);
+                           unsigned int site, double p, void* dqkv, float* dkv_acc, long long rows,
+                           void* stream);
 
 /* Backward of y = LayerNorm(s)*gamma + beta on bf16 rows: dx (bf16), dgamma / dbeta accumulated into
  * f32 buffers (either may be NULL).  width in {256,512,768,1024}. */

@@ -94,11 +94,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // 64-key blocks as one flat item list with a two-deep cp.async pipeline (the next item's K/V - and the
 // next head's Q - stream in while the current item is computed), so the global-load latency is paid
 // once per CTA instead of once per head.
-template <int BLOCK_M>
+template <int BLOCK_M, bool DROP>
 __global__ void __launch_bounds__(BLOCK_M * 2, BLOCK_M == 64 ? 4 : 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask_bias,
                  const int* __restrict__ seq_off, int S_max, int heads, int hpg,
-                 __nv_bfloat16* __restrict__ out) {
+                 __nv_bfloat16* __restrict__ out, DropCfg drop) {
     constexpr int NT = BLOCK_M * 2;
     constexpr int QBYTES = BLOCK_M * 128, KVBYTES = kBlockN * 128;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -276,6 +276,19 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
             l1 += s[j][2] + s[j][3];
         }
 
+        if (DROP) {
+            // train mode: the probabilities that feed P V are dropped / rescaled; l0 / l1 above stay undropped
+            const unsigned long long row_idx =
+                (static_cast<unsigned long long>(b * heads + h_begin + hh) * S_max + (q0 + warp * 16 + g)) * S_max;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned long long k0 = static_cast<unsigned long long>(kb * kBlockN + j * 8 + tq * 2);
+                s[j][0] = drop_keep(drop, row_idx + k0) ? s[j][0] * drop.scale : 0.0f;
+                s[j][1] = drop_keep(drop, row_idx + k0 + 1) ? s[j][1] * drop.scale : 0.0f;
+                s[j][2] = drop_keep(drop, row_idx + 8ull * S_max + k0) ? s[j][2] * drop.scale : 0.0f;
+                s[j][3] = drop_keep(drop, row_idx + 8ull * S_max + k0 + 1) ? s[j][3] * drop.scale : 0.0f;
+            }
+        }
         // ---- O += P V
         const uint32_t vt = v_s + buf * KVBYTES;
 #pragma unroll
@@ -331,12 +344,12 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
     }
 }
 
-template <int BLOCK_M>
+template <int BLOCK_M, bool DROP>
 int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
-           int heads, __nv_bfloat16* out, cudaStream_t stream) {
+           int heads, __nv_bfloat16* out, cudaStream_t stream, DropCfg drop = DropCfg{0ull, 0u, 0u, 1.0f}) {
     constexpr int SMEM = 2 * BLOCK_M * 128 + 4 * kBlockN * 128 + kMaxS * 4 + 64;
     static bool attr_set = false;
-    auto kfn = attention_kernel<BLOCK_M>;
+    auto kfn = attention_kernel<BLOCK_M, DROP>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) {
@@ -351,7 +364,7 @@ int launch(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off,
     while (hpg > 1 && base * ((heads + hpg - 1) / hpg) < 148LL * 8) hpg = (hpg + 1) / 2;
     if (hpg > 4) hpg = 4;
     dim3 grid((S + BLOCK_M - 1) / BLOCK_M, (heads + hpg - 1) / hpg, B);
-    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, seq_off, S, heads, hpg, out);
+    kfn<<<grid, BLOCK_M * 2, SMEM, stream>>>(qkv, mask_bias, seq_off, S, heads, hpg, out, drop);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention_kernel<%d> launch: %s", BLOCK_M, cudaGetErrorString(e));
@@ -614,10 +627,7 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
                       int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc,
                       int blocked, const DropCfg* drop) {
     if (B <= 0 || S <= 0) return 0;
-    if (drop && drop->thresh != 0u && !(S <= 128 && g_attention_tc)) {
-        set_last_error("attention_forward: dropout on the probabilities is implemented on the tcgen05 path (S <= 128)");
-        return -1;
-    }
+    const bool dropping = drop && drop->thresh != 0u;
     if (blocked && !(S <= 128 && g_attention_tc)) {
         set_last_error("attention_forward: the blocked qkv layout is only read by the tcgen05 path (S <= 128)");
         return -1;
@@ -633,9 +643,13 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     if (S <= 128 && g_attention_tc && static_cast<long long>(B) * heads < 0x7fffffffLL)
         return launch_tc(qkv, mask_bias, seq_off, B, S, heads,
                          rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream, drop);
+    if (dropping) {
+        if (S > 64) return launch<128, true>(qkv, mask_bias, seq_off, B, S, heads, out, stream, *drop);
+        return launch<64, true>(qkv, mask_bias, seq_off, B, S, heads, out, stream, *drop);
+    }
     if (S > 64)
-        return launch<128>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
-    return launch<64>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
+        return launch<128, false>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
+    return launch<64, false>(qkv, mask_bias, seq_off, B, S, heads, out, stream);
 }
 
 }  // namespace mrd

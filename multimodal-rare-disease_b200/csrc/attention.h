@@ -20,7 +20,7 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
                       int S, int heads, __nv_bfloat16* out, cudaStream_t stream,
                       long long rows_alloc = 0, int blocked = 0, const struct DropCfg* drop = nullptr);
 // drop (train mode): dropout on the attention probabilities, element index ((b*heads + h)*S + q)*S + k
-// (rng.cuh); attention_backward (train_kernels.h) recomputes the same mask.  S <= 128 only.
+// (rng.cuh); attention_backward (train_kernels.h) recomputes the same mask.
 // blocked = 1: qkv is [3*heads][rows_alloc][64] (what plan_gemm(c_blocked=1) writes): each head's Q, K
 // and V tile is one contiguous block - streaming-friendly for the TMA loads of the tcgen05 path.
 bool attention_prefers_blocked_qkv(int S);

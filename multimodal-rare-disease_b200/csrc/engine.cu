@@ -1469,10 +1469,20 @@ int mrd_dropout_mask(unsigned long long seed, unsigned int site, double p, long 
 
 int mrd_attention_bwd_bf16(const void* qkv, const void* ctx, const void* dctx, const float* mask_bias,
                            const int* seq_off, int B, int S, int heads, unsigned long long seed,
-                           unsigned int site, double p, void* dqkv, void* stream) {
-    return attention_backward(static_cast<const bf16*>(qkv), static_cast<const bf16*>(ctx),
-                              static_cast<const bf16*>(dctx), mask_bias, seq_off, B, S, heads,
-                              make_drop(seed, site, p), static_cast<bf16*>(dqkv), static_cast<cudaStream_t>(stream));
+                           unsigned int site, double p, void* dqkv, float* dkv_acc, long long rows, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MRD_TRY(attention_backward(static_cast<const bf16*>(qkv), static_cast<const bf16*>(ctx),
+                               static_cast<const bf16*>(dctx), mask_bias, seq_off, B, S, heads,
+                               make_drop(seed, site, p), static_cast<bf16*>(dqkv), s, dkv_acc));
+    if (S > 128) {   // fold the fp32 dK | dV accumulators into dqkv's K / V columns
+        const int Hd = heads * 64;
+        if (rows <= 0 || rows > 0x7fffffffLL) {
+            set_last_error("mrd_attention_bwd_bf16: rows (of qkv / dqkv / dkv_acc) is required when S > 128");
+            return -1;
+        }
+        return cast_f32_to_bf16(dkv_acc, 2 * Hd, static_cast<int>(rows), 2 * Hd, static_cast<bf16*>(dqkv) + Hd, 3 * Hd, s);
+    }
+    return 0;
 }
 
 int mrd_attention_train_bf16(const void* qkv, const float* mask_bias, int B, int S, int heads,

@@ -61,6 +61,7 @@ struct TrainState {
     GemmLaunch w_f2, w_f1, w_o, w_qkv;    // dW = dY^T X on the shared staging buffers
     bf16 *x_final = nullptr, *z = nullptr, *dxa = nullptr, *dxb = nullptr, *d_s = nullptr, *dz = nullptr,
          *dh1 = nullptr, *dctx = nullptr, *dbig = nullptr, *dqkv = nullptr, *At = nullptr, *Bt = nullptr;
+    float* dkv_acc = nullptr;             // [Ta, 2*Hd] fp32: dK / dV accumulator of the tiled attention backward (S > 128)
     float* wq_scratch = nullptr;          // [3*Hd, Hd] fp32: QKV weight gradient before it is split
     float* bq_scratch = nullptr;          // [3*Hd]
     // batch-level fp32 activations
@@ -181,7 +182,7 @@ int train_ensure_plan(mrd_ctx* c, int B, int S) {
     total += nl * (5 * pad1k(Ta * Hd, 2) + pad1k(Ta * 3 * Hd, 2) + 2 * pad1k(Ta * F, 2));  // saved per layer
     total += 8 * pad1k(Ta * Hd, 2) + pad1k(Ta * F, 2) + pad1k(Ta * 3 * Hd, 2);             // x_final + temporaries
     total += 2 * pad1k(1LL * wide * Tp, 2);                                                 // At, Bt
-    total += pad1k(3LL * Hd * Hd, 4) + pad1k(3LL * Hd, 4);
+    total += pad1k(3LL * Hd * Hd, 4) + pad1k(3LL * Hd, 4) + (S > 128 ? pad1k(Ta * 2 * Hd, 4) : 0);
     const long long bw = 2048;
     const size_t n_head = c->head_hidden.size();
     total += (17 + n_head + 5) * pad1k(1LL * B * bw, 4);
@@ -212,6 +213,7 @@ int train_ensure_plan(mrd_ctx* c, int B, int S) {
     t->dqkv = arena_take<bf16>(&t->ws, Ta * 3 * Hd);
     t->At = arena_take<bf16>(&t->ws, 1LL * wide * Tp);
     t->Bt = arena_take<bf16>(&t->ws, 1LL * wide * Tp);
+    t->dkv_acc = S > 128 ? arena_take<float>(&t->ws, Ta * 2 * Hd) : nullptr;
     t->wq_scratch = arena_take<float>(&t->ws, 3LL * Hd * Hd);
     t->bq_scratch = arena_take<float>(&t->ws, 3LL * Hd);
     float** fb[] = {&t->pooled, &t->a1, &t->p1, &t->img, &t->cls, &t->txt, &t->ip, &t->tp, &t->v1, &t->v1d,
@@ -535,9 +537,8 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
         set_last_error("training step needs cnn_encoder, text_encoder, fusion and classifier weights");
         return -3;
     }
-    if (S > 128 || S <= 0) {
-        set_last_error("training step: sequence length %d unsupported (1..128; the attention backward is a single "
-                       "128x128 tile)", S);
+    if (S > 512 || S <= 0 || S > c->max_pos) {
+        set_last_error("training step: sequence length %d unsupported (1..%d)", S, c->max_pos < 512 ? c->max_pos : 512);
         return -1;
     }
     if (B > c->img_chunk || 1LL * B * S > c->tok_chunk) {
@@ -778,8 +779,11 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         if (float* gw = grad_of(gt, pre + "attention.output.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_o, dz, Hd, b.ctx, Hd, gw, s));
         if (float* gb = grad_of(gt, pre + "attention.output.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
         MRD_TRY(run(c, "train.dgrad", dz == t->dz ? p.d_ctx : p.d_ctx0, s));
+        if (t->dkv_acc) cudaMemsetAsync(t->dkv_acc, 0, sizeof(float) * static_cast<size_t>(T) * 2 * Hd, s);
         TRK("train.attention_bwd", CAT_ATTN, attention_backward(b.qkv, b.ctx, t->dctx, c->t_bias, c->t_seq_off, B, S, c->bert_heads,
-                                   make_drop(seed, site_attn(i), o.p_bert_attn), t->dqkv, s));
+                                   make_drop(seed, site_attn(i), o.p_bert_attn), t->dqkv, s, t->dkv_acc));
+        if (t->dkv_acc)   // fp32 dK | dV accumulators -> the K / V columns of dqkv
+            TRK("train.attention_bwd", CAT_MEM, cast_f32_to_bf16(t->dkv_acc, 2 * Hd, T, 2 * Hd, t->dqkv + Hd, 3 * Hd, s));
         // QKV: one [3*Hd, Hd] product, split into the three parameters (the query block carries the
         // folded 1/sqrt(64): d/dWq = 0.125 * d/dWq')
         float* gq = grad_of(gt, pre + "attention.self.query.weight");

@@ -88,13 +88,17 @@ int embed_ln_bwd(const long long* ids, const int* row_tok, int rows, const int* 
                  float* dtype0, float* dgamma, float* dbeta, cudaStream_t s);
 
 // ---- attention backward --------------------------------------------------------------------------
-// Backward of softmax(Q K^T + key_bias) V with optional dropout on the probabilities, sequences of at
-// most 128 tokens (one 128x128 tile per (sample, head), mma.sync m16n8k16).  qkv / dqkv: [rows, 3*heads*64]
+// Backward of softmax(Q K^T + key_bias) V with optional dropout on the probabilities (mma.sync m16n8k16).
+// Sequences of at most 128 tokens: one 128x128 tile per (sample, head).  qkv / dqkv: [rows, 3*heads*64]
 // bf16 token-major (Q already scaled by 1/sqrt(64): dQ is the gradient of the scaled Q); ctx = forward
 // output O, dctx = its gradient: [rows, heads*64].  Layout arguments as attention_forward.
+// S > 128 (up to 512): tiled over 128-query x 128-key blocks with the softmax statistics recomputed in a first
+// pass; dK / dV are ACCUMULATED in fp32 into dkv_acc [rows, 2*heads*64] (K then V; zeroed by the caller) because
+// several query blocks contribute to one key block - the caller converts them into dqkv's K / V columns; dQ is
+// written to dqkv directly.  dkv_acc may be null when S <= 128.
 int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
                        const float* mask_bias, const int* seq_off, int B, int S, int heads, DropCfg d,
-                       __nv_bfloat16* dqkv, cudaStream_t s);
+                       __nv_bfloat16* dqkv, cudaStream_t s, float* dkv_acc = nullptr);
 
 // ---- BatchNorm with batch statistics (frozen backbone under model.train(), TV:models/resnet.py:143-163) --
 // sum[c] += sum_r y[r,c], sumsq[c] += sum_r y[r,c]^2 over an NHWC bf16 tensor viewed as [rows, C]; C % 2 == 0.

@@ -64,7 +64,10 @@ def _attention_ref(qkv, bias, B, S, heads, dctx, mask=None, p=0.0):
 
 
 @pytest.mark.parametrize("B,S,lens,p", [(3, 128, [128, 77, 5], 0.0), (4, 48, [48, 48, 17, 1], 0.0),
-                                        (2, 128, [128, 100], 0.1), (5, 32, [32, 9, 32, 20, 31], 0.25)])
+                                        (2, 128, [128, 100], 0.1), (5, 32, [32, 9, 32, 20, 31], 0.25),
+                                        # > 128 tokens: tiled backward (fp32 dK/dV accumulation), mma.sync forward
+                                        (3, 256, [256, 130, 3], 0.0), (2, 200, [200, 129], 0.1),
+                                        (2, 512, [512, 385], 0.0), (1, 384, [300], 0.2)])
 def test_attention_backward_vs_autograd(cuda, lib, B, S, lens, p):
     heads = 12
     g = torch.Generator().manual_seed(5)
@@ -89,8 +92,10 @@ def test_attention_backward_vs_autograd(cuda, lib, B, S, lens, p):
     err_o = (out.float()[live] - o_ref[live]).norm() / o_ref[live].norm()
     assert err_o.item() <= 1e-2, err_o.item()
     dqkv = torch.zeros_like(qkv)
+    acc = torch.zeros(B * S, 2 * heads * 64, device=cuda) if S > 128 else None
     assert lib.mrd_attention_bwd_bf16(_p(qkv), _p(out), _p(dctx), _p(bias), None, B, S, heads, C.c_ulonglong(seed),
-                                      site, p, _p(dqkv), _stream()) == 0, lib.mrd_last_error()
+                                      site, p, _p(dqkv), None if acc is None else _p(acc), B * S,
+                                      _stream()) == 0, lib.mrd_last_error()
     torch.cuda.synchronize()
     # padded QUERY rows are outputs nobody reads: the engine never feeds them a gradient; here they do get
     # one, so compare everything (keys beyond the length receive exactly zero dK/dV in both)
@@ -116,11 +121,11 @@ def test_attention_backward_packed_layout(cuda, lib):
     dctx[(bias == float("-inf")).view(B * S).cpu()] = 0   # padded queries do not exist in the packed layout
     d_dense = torch.zeros_like(qkv)
     assert lib.mrd_attention_bwd_bf16(_p(qkv), _p(ctx), _p(dctx), _p(bias), None, B, S, heads, C.c_ulonglong(1), 0,
-                                      0.0, _p(d_dense), _stream()) == 0
+                                      0.0, _p(d_dense), None, B * S, _stream()) == 0
     pq, pc, pd = qkv[rows].contiguous(), ctx[rows].contiguous(), dctx[rows].contiguous()
     d_pack = torch.zeros_like(pq)
     assert lib.mrd_attention_bwd_bf16(_p(pq), _p(pc), _p(pd), None, _p(off), B, S, heads, C.c_ulonglong(1), 0, 0.0,
-                                      _p(d_pack), _stream()) == 0
+                                      _p(d_pack), None, pq.shape[0], _stream()) == 0
     torch.cuda.synchronize()
     assert torch.equal(d_pack, d_dense[rows])
 
@@ -383,6 +388,42 @@ def test_backward_only_linear_loss_sensitised(cuda):
 # the unmodified reference on this batch, dropout 0, lr 2e-4 (oracle/ref_train_loop.py)
 REF_LOOP = [2.289, 2.268, 2.241, 2.212, 2.176, 2.161, 2.111, 2.054, 1.997, 1.932, 1.914, 1.827, 1.829, 1.706,
             1.645, 1.562, 1.869, 1.583, 1.462, 1.384]
+
+
+def test_train_step_long_sequences(cuda, sens):
+    """256 tokens (what the reference's multimodal trainer tokenises to, src/train_multimodal.py:53): mma.sync
+    forward with dropout-capable probabilities, tiled attention backward; dropout on, library masks to the oracle."""
+    B, S = 2, 256
+    model = _train_model(sens, zero_dropout=False)
+    images, ids, mask = synth.make_inputs(B, S, 81, None, H=64, W=64)
+    labels = torch.tensor([5, 0])
+    torch.manual_seed(78)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    torch.manual_seed(78)
+    out = model(images.cuda(), ids.cuda(), mask.cuda())
+    loss = F.cross_entropy(out["logits"], labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    masks = _export_masks(lib_handle(), model, seed, B, S, model._train_options())
+    ref_loss, g32 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels, masks=masks)
+    _, g16 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels, masks=masks, autocast=True)
+    assert abs(loss.item() - ref_loss) <= 2e-3 * abs(ref_loss), (loss.item(), ref_loss)
+    named = dict(model.named_parameters())
+    _compare_with_floor({k: named[k].grad.float().cpu() for k in g32}, g32, g16, "256-token step")
+    # padded variant: 2 sequences of 200 / 131 tokens in a 256-token batch, no dropout, vs the fp32 oracle
+    model2 = _train_model(sens)
+    images, ids, mask = synth.make_inputs(B, S, 82, [200, 131], H=64, W=64)
+    out = model2(images.cuda(), ids.cuda(), mask.cuda())
+    F.cross_entropy(out["logits"], labels.cuda()).backward()
+    _, g32 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels)
+    _, g16 = _oracle_grads_gpu(sens, images, ids, mask, labels=labels, autocast=True)
+    named = dict(model2.named_parameters())
+    _compare_with_floor({k: named[k].grad.float().cpu() for k in g32}, g32, g16, "256-token padded step")
+
+
+def lib_handle():
+    from importlib import import_module
+    return import_module("multimodal-rare-disease_b200._lib").load()
 
 
 def test_training_loop_follows_reference(cuda):

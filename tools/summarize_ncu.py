@@ -22,7 +22,9 @@ cmd_note = sys.argv[2] if len(sys.argv) > 2 else ""
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 
-lp = os.path.join(ROOT, "gpurun_out", "launches.csv")
+# optional: MRD_NCU_LIST / MRD_NCU_REP = other input files under gpurun_out/, MRD_NCU_SUFFIX = output name suffix
+lp = os.path.join(ROOT, "gpurun_out", os.environ.get("MRD_NCU_LIST", "launches.csv"))
+sfx = os.environ.get("MRD_NCU_SUFFIX", "")
 if os.path.exists(lp):
     rows = list(csv.reader(open(lp)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -47,14 +49,14 @@ if os.path.exists(lp):
         elif r[mn] == "dram__bytes_write.sum":
             a["wr"] += v
     tot = sum(a["ns"] for a in agg.values())
-    with open(os.path.join(out, f"{tag}_launches_by_kernel.csv"), "w") as fh:
+    with open(os.path.join(out, f"{tag}{sfx}_launches_by_kernel.csv"), "w") as fh:
         fh.write("kernel,launches,total_us,share_of_all_launches,dram_read_MB_per_launch,dram_write_MB_per_launch\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
             n = max(a["n"], 1)
             fh.write(f'{k},{a["n"]},{a["ns"] / 1e3:.1f},{a["ns"] / tot:.4f},{a["rd"] / n / 1e6:.3f},{a["wr"] / n / 1e6:.3f}\n')
     fam = [a for k, a in agg.items() if k.startswith("conv_gemm_kernel")]
     n = sum(a["n"] for a in fam)
-    if n:
+    if n and not sfx:
         tr = {"kernel": "conv_gemm_kernel (all instantiations)", "launches_captured": n,
               "dram_bytes_per_launch": (sum(a["rd"] for a in fam) + sum(a["wr"] for a in fam)) / n,
               "dram_read_bytes_per_launch": sum(a["rd"] for a in fam) / n,
@@ -66,7 +68,7 @@ if os.path.exists(lp):
             json.dump(tr, fh, indent=1)
     print("launch list:", sum(a["n"] for a in agg.values()), "launches,", f"{tot / 1e6:.2f} ms")
 
-rp = os.path.join(ROOT, "gpurun_out", "prof_gemm.ncu-rep")
+rp = os.path.join(ROOT, "gpurun_out", os.environ.get("MRD_NCU_REP", "prof_gemm.ncu-rep"))
 if os.path.exists(rp):
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -78,7 +80,7 @@ if os.path.exists(rp):
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
-    with open(os.path.join(out, f"{tag}_gemm_full.csv"), "w") as fh:
+    with open(os.path.join(out, f"{tag}{sfx}_{'gemm' if not sfx else 'kernels'}_full.csv"), "w") as fh:
         fh.write(",".join(w for w, _ in idx) + "\n")
         fh.write(",".join(rows[1][i] for _, i in idx) + "\n")  # units
         for r in rows[2:]:
