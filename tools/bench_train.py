@@ -100,7 +100,9 @@ def main():
     ms_step = ms / args.steps
     line = None
     if rank == 0:
-        # one profiled step: device time per label of the LIBRARY's kernels (the optimizer and the loss are torch's)
+        # one profiled step: device time per label of the LIBRARY's kernels (the optimizer and the loss are torch's).
+        # Rank 0 runs it alone, so the gradient all-reduce must be off for it (the other ranks are not in this step).
+        model.data_parallel(False)
         eng.profile(True)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         opt.zero_grad(set_to_none=True)
