@@ -44,7 +44,7 @@ class B200Module(nn.Module):
         if eng is None or eng.device != dev:
             eng = Engine(dev, self._mrd_options())
             self.__dict__["_mrd_engine"] = eng
-        eng.sync_weights(self._mrd_named())
+        eng.sync_weights(self._mrd_named(), training=allow_training and self.training)
         return eng
 
     def configure_b200(self, img_chunk: int = 0, seq_chunk_tokens: int = 0, fp32_check=None) -> None:

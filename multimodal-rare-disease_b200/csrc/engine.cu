@@ -164,6 +164,7 @@ struct mrd_ctx {
 
     // ---- weights
     bool has_cnn = false, has_text = false, has_fusion = false, has_head = false;
+    bool has_backbone = false, has_proj = false;   // has_cnn = both (they are handed over as separate groups)
     bf16* stem_w = nullptr;
     float* stem_b = nullptr;
     std::vector<Bottleneck> blocks;
@@ -346,6 +347,15 @@ int load_vec(mrd_ctx* c, const Table& t, const std::string& name, float** out, c
     return 0;
 }
 
+int load_cnn_projection(mrd_ctx* c, const Table& t, cudaStream_t s) {
+    MRD_TRY(load_linear(c, t, "cnn_encoder.projection.0", &c->proj1, s));
+    MRD_TRY(load_linear(c, t, "cnn_encoder.projection.3", &c->proj2, s));
+    c->img_emb_dim = c->proj2.out;
+    c->has_proj = true;
+    c->has_cnn = c->has_backbone && c->has_proj;
+    return 0;
+}
+
 int load_cnn(mrd_ctx* c, const Table& t, cudaStream_t s) {
     const std::string bb = "cnn_encoder.backbone.";
     {
@@ -391,10 +401,8 @@ int load_cnn(mrd_ctx* c, const Table& t, cudaStream_t s) {
     }
     c->blocks.resize(bi);
     c->feat_dim = c->blocks.back().c3.cout;
-    MRD_TRY(load_linear(c, t, "cnn_encoder.projection.0", &c->proj1, s));
-    MRD_TRY(load_linear(c, t, "cnn_encoder.projection.3", &c->proj2, s));
-    c->img_emb_dim = c->proj2.out;
-    c->has_cnn = true;
+    c->has_backbone = true;
+    c->has_cnn = c->has_backbone && c->has_proj;
     return 0;
 }
 
@@ -1216,7 +1224,7 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Table t;
     t.m.reserve(static_cast<size_t>(n) * 2);
-    bool any_cnn = false, any_text = false, any_fusion = false, any_head = false;
+    bool any_cnn = false, any_proj = false, any_text = false, any_fusion = false, any_head = false;
     for (int i = 0; i < n; ++i) {
         Tensor x;
         x.p = static_cast<const float*>(ptrs[i]);
@@ -1227,7 +1235,8 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
         rt.p = x.p;
         for (int j = 0; j < 4; ++j) rt.d[j] = x.d[j];
         c->raw[nm] = rt;
-        any_cnn |= nm.rfind("cnn_encoder.", 0) == 0;
+        any_cnn |= nm.rfind("cnn_encoder.backbone.", 0) == 0;
+        any_proj |= nm.rfind("cnn_encoder.projection.", 0) == 0;
         any_text |= nm.rfind("text_encoder.", 0) == 0;
         any_fusion |= nm.rfind("fusion.", 0) == 0;
         any_head |= nm.rfind("classifier.", 0) == 0;
@@ -1236,8 +1245,9 @@ int mrd_ctx_load_weights(mrd_ctx* c, int n, const char* const* names, const void
     cudaError_t e = c->load_sync ? cudaDeviceSynchronize() : cudaSuccess;
     if (e != cudaSuccess) return cuda_fail(e, "mrd_ctx_load_weights: device sync");
     const size_t n_blocks = c->blocks.size(), n_layers = c->layers.size(), n_head = c->head_hidden.size();
-    if (c->train) train_invalidate_packs(c);
+    if (c->train) train_invalidate_packs(c, any_text, any_cnn);
     if (any_cnn) MRD_TRY(load_cnn(c, t, s));
+    if (any_proj) MRD_TRY(load_cnn_projection(c, t, s));
     if (any_text) MRD_TRY(load_text(c, t, s));
     if (any_fusion) MRD_TRY(load_fusion(c, t, s));
     if (any_head) MRD_TRY(load_head(c, t, s));
@@ -1381,9 +1391,9 @@ int mrd_multimodal_fwd(mrd_ctx* c, const void* images, int img_dtype, const long
         MRD_TRY(fp32_fusion(c->raw, o, &c->f32_ws, ie, te, B, fe, attn_i2t, attn_t2i, s));
         return fp32_head(c->raw, o, &c->f32_ws, fe, B, logits, probs, s);
     }
-    MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, nullptr, nullptr, s));
     BatchPlan* bp;
     MRD_TRY(get_batch_plan(c, B, &bp));
+    MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, nullptr, nullptr, s));
     MRD_TRY(run_projection(c, bp, img_emb, s));
     MRD_TRY(run_bert(c, ids, mask, mask_dtype, B, S, txt_emb, nullptr, nullptr, s));
     MRD_TRY(run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s));

@@ -91,10 +91,10 @@ TrainState* train_state(mrd_ctx* c) {
 void train_cnn_invalidate(TrainState* t);
 void train_cnn_free(TrainState* t);
 
-void train_invalidate_packs(mrd_ctx* c) {
+void train_invalidate_packs(mrd_ctx* c, bool text, bool backbone) {
     if (!c->train) return;
-    c->train->packs_valid = false;
-    train_cnn_invalidate(c->train);
+    if (text) c->train->packs_valid = false;
+    if (backbone) train_cnn_invalidate(c->train);
 }
 
 void train_free(mrd_ctx* c) {

@@ -511,7 +511,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 }
 
 template <int BLOCK_N, int MODE>
-int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
+int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
     auto kfn = conv_gemm_kernel<BLOCK_N, MODE>;
@@ -528,13 +528,25 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream) {
                          ? C::FIXED + g->p.stages * g->p.a_stage_bytes + g->p.b_res_bytes
                          : C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g->grid);
+    int grid = g->grid;
+    if (sm_limit > 0 && grid > sm_limit) {
+        // the kernel is persistent (tiles strided by gridDim): a smaller grid leaves SMs to a kernel of another
+        // stream.  Weights-resident modes need a multiple of n_tiles_n CTAs.
+        grid = sm_limit;
+        if (MODE != MODE_GENERIC) {
+            grid = grid / g->p.n_tiles_n * g->p.n_tiles_n;
+            if (grid < g->p.n_tiles_n) grid = g->p.n_tiles_n;
+        }
+    }
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    // no programmatic dependent launch under an SM cap: the early-launched CTAs of the next kernel would sit on
+    // the SMs that the cap leaves to the other stream
+    attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && sm_limit <= 0) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, g->p);
@@ -1008,20 +1020,20 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
     return finish_plan(g, 64);
 }
 
-int launch_gemm(const GemmLaunch* g, cudaStream_t stream) {
-    if (g->stem) return launch_variant<64, MODE_STEM>(g, stream);
+int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
+    if (g->stem) return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
     if (g->flat3) {
         switch (g->block_n) {
-            case 64: return launch_variant<64, MODE_FLAT3>(g, stream);
-            case 128: return launch_variant<128, MODE_FLAT3>(g, stream);
+            case 64: return launch_variant<64, MODE_FLAT3>(g, stream, sm_limit);
+            case 128: return launch_variant<128, MODE_FLAT3>(g, stream, sm_limit);
         }
         set_last_error("launch_gemm: bad flat3 block_n %d", g->block_n);
         return -1;
     }
     switch (g->block_n) {
-        case 64: return launch_variant<64, MODE_GENERIC>(g, stream);
-        case 128: return launch_variant<128, MODE_GENERIC>(g, stream);
-        case 256: return launch_variant<256, MODE_GENERIC>(g, stream);
+        case 64: return launch_variant<64, MODE_GENERIC>(g, stream, sm_limit);
+        case 128: return launch_variant<128, MODE_GENERIC>(g, stream, sm_limit);
+        case 256: return launch_variant<256, MODE_GENERIC>(g, stream, sm_limit);
     }
     set_last_error("launch_gemm: bad block_n %d", g->block_n);
     return -1;

@@ -101,7 +101,10 @@ int plan_stem(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W,
 int plan_gemm_splitk(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K,
                      const __nv_bfloat16* W, int N, float* out_f32, long long ld_f32, const int* dyn_k);
 
-int launch_gemm(const GemmLaunch* g, cudaStream_t stream);
+// sm_limit > 0 caps the grid (the kernel is persistent, so any grid size covers all tiles).  Used by the
+// branch-overlap experiment (ResNet and BERT side by side on disjoint SM sets, DESIGN.md section 5: slower,
+// not shipped); kept because it costs nothing.
+int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit = 0);
 
 int gemm_num_sms();
 

@@ -47,7 +47,9 @@ class Engine:
                 "there is no CPU fallback - use the reference implementation on CPU")
         self.lib = _lib.load()
         self.device = device
-        self._sig = None
+        self._sigs: Dict[str, tuple] = {}
+        self._dirty = set()
+        self._keep: Dict[str, list] = {}
         self._ctx = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(self.lib.mrd_ctx_create(C.byref(self._ctx)), "mrd_ctx_create")
@@ -99,40 +101,67 @@ class Engine:
         return int(self.lib.mrd_ctx_device_bytes(self._ctx))
 
     # ------------------------------------------------------------------ weights
-    def sync_weights(self, named: Iterable[Tuple[str, torch.Tensor]]) -> bool:
-        """Re-pack the library's weights iff a tensor was replaced or written since the last call.
+    # parameter groups that are re-packed independently (a training step changes the trainable ones only: the
+    # frozen ResNet50 backbone - 53 BN-folded filters - is not re-packed every step)
+    GROUPS = ("cnn_encoder.backbone.", "cnn_encoder.projection.", "text_encoder.", "fusion.", "classifier.")
 
-        named: (canonical state_dict name, tensor) pairs.  Returns True when a re-pack happened.
-        """
-        named = [(n, t) for n, t in named if t.is_floating_point()]
-        sig = tuple((n, t.data_ptr(), t._version, t.dtype) for n, t in named)
-        if sig == self._sig:
+    def mark_dirty(self, group: str) -> None:
+        """The library changed tensors of `group` behind torch's back (running statistics of the batch-norm
+        layers in train mode): the next eval-mode hand-over re-packs the group."""
+        self._dirty.add(group)
+
+    def sync_weights(self, named: Iterable[Tuple[str, torch.Tensor]], training: bool = False) -> bool:
+        """Re-pack the library's weights for every group in which a tensor was replaced or written since the
+        last call.  named: (canonical state_dict name, tensor) pairs.  Returns True when a re-pack happened.
+        training=True leaves a merely `dirty` backbone alone (its folded eval-mode copy is not used there)."""
+        groups = {g: [] for g in self.GROUPS}
+        for n, t in named:
+            if not t.is_floating_point():
+                continue
+            for g in self.GROUPS:
+                if n.startswith(g):
+                    groups[g].append((n, t))
+                    break
+        changed = []
+        for g, items in groups.items():
+            if not items:
+                continue
+            sig = tuple((n, t.data_ptr(), t._version, t.dtype) for n, t in items)
+            if sig != self._sigs.get(g) or (g in self._dirty and not training):
+                changed.append((g, items, sig))
+        if not changed:
             return False
-        keep = []  # fp32 contiguous views / temporaries alive until the packing kernels finished
-        n = len(named)
+        todo = [it for _, items, _ in changed for it in items]
+        n = len(todo)
         names = (C.c_char_p * n)()
         ptrs = (C.c_void_p * n)()
         shapes = (C.c_longlong * (4 * n))()
-        for i, (name, t) in enumerate(named):
-            if t.device != self.device:
-                raise _lib.MrdError(f"parameter {name} is on {t.device}, engine is on {self.device}")
-            if t.dim() > 4:
-                raise _lib.MrdError(f"parameter {name} has {t.dim()} dims")
-            x = t.detach()
-            if x.dtype != torch.float32 or not x.is_contiguous():
-                x = x.float().contiguous()
-            keep.append(x)
-            names[i] = name.encode()
-            ptrs[i] = x.data_ptr()
-            for j, d in enumerate(x.shape):
-                shapes[4 * i + j] = d
+        keep = {g: [] for g, _, _ in changed}
+        i = 0
+        for g, items, _ in changed:
+            for name, t in items:
+                if t.device != self.device:
+                    raise _lib.MrdError(f"parameter {name} is on {t.device}, engine is on {self.device}")
+                if t.dim() > 4:
+                    raise _lib.MrdError(f"parameter {name} has {t.dim()} dims")
+                x = t.detach()
+                if x.dtype != torch.float32 or not x.is_contiguous():
+                    x = x.float().contiguous()
+                keep[g].append(x)
+                names[i] = name.encode()
+                ptrs[i] = x.data_ptr()
+                for j, d in enumerate(x.shape):
+                    shapes[4 * i + j] = d
+                i += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mrd_ctx_load_weights(self._ctx, n, names, ptrs, shapes,
                                                      _stream(self.device)), "mrd_ctx_load_weights")
-        self._sig = sig
-        # the fp32 check mode and the training step read the raw fp32 tensors handed over above: keep
-        # them (views of the parameters, or fp32 copies of non-fp32 ones) alive until the next hand-over
-        self._keep = keep
+        for g, _, sig in changed:
+            self._sigs[g] = sig
+            self._dirty.discard(g)
+            # the fp32 check mode and the training step read the raw fp32 tensors handed over above: keep them
+            # (views of the parameters, or fp32 copies of non-fp32 ones) alive until the group's next hand-over
+            self._keep[g] = keep[g]
         return True
 
     # ------------------------------------------------------------------ input normalisation

@@ -206,7 +206,7 @@ class MultimodalClassifier(B200Module):
                         if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
             if counters:
                 torch._foreach_add_(counters, 1)
-            eng._sig = None
+            eng.mark_dirty("cnn_encoder.backbone.")
         return {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
 
     def data_parallel(self, enabled: bool = True, process_group=None) -> "MultimodalClassifier":

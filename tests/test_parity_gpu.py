@@ -296,3 +296,4 @@ def test_all_hidden_states_vs_oracle(cuda, state):
         assert _rel_rows(last[b, :L], ref_last[b, :L]) <= REL_TOL
     # intermediate layers differ from their neighbours (really per-layer, not copies)
     assert not torch.equal(states[5], states[6])
+

@@ -512,6 +512,40 @@ def test_train_step_batchnorm_batch_statistics(cuda, sens):
     assert (e1.cpu() - want).abs().max().item() <= 2e-2
 
 
+def test_reference_amp_loop_shape_works(cuda, sens):
+    """The reference's trainers wrap the step in fp16 autocast + GradScaler when use_amp is on
+    (src/train.py:258-311, src/train_multimodal.py:518-530).  The drop-in computes in bf16/fp32 regardless; the
+    wrappers must stay harmless: scaled loss -> scaled dlogits -> gradients linear in them -> unscale_ restores
+    the same gradients as the plain loop."""
+    images, ids, mask = synth.make_inputs(4, 32, 41, [32, 20, 7, 1], H=64, W=64)
+    labels = torch.tensor([3, 1, 7, 3]).cuda()
+    args = (images.cuda(), ids.cuda(), mask.cuda())
+    plain = _train_model(sens)
+    nn.CrossEntropyLoss()(plain(*args)["logits"], labels).backward()
+    amp = _train_model(sens)
+    opt = torch.optim.AdamW(amp.parameters(), lr=5e-5, weight_decay=0.05)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    with torch.amp.autocast("cuda"):
+        out = amp(images=args[0], input_ids=args[1], attention_mask=args[2])
+        loss = nn.CrossEntropyLoss()(out["logits"], labels)
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    total = nn.utils.clip_grad_norm_(amp.parameters(), 1.0)
+    scaler.step(opt)
+    scaler.update()
+    assert torch.isfinite(total) and scaler.get_scale() == 1024.0      # no overflow was detected
+    num = den = 0.0
+    coef = min(1.0, 1.0 / (total.item() + 1e-6))
+    for (k, p), (_, q) in zip(plain.named_parameters(), amp.named_parameters()):
+        if p.grad is None:
+            assert q.grad is None
+            continue
+        num += (q.grad / coef - p.grad).double().pow(2).sum().item()
+        den += p.grad.double().pow(2).sum().item()
+    # dlogits are rounded differently (x1024 before the bf16 gradient stream), nothing else differs
+    assert (num / den) ** 0.5 <= 2e-2, (num / den) ** 0.5
+
+
 def test_train_mode_refuses_what_it_cannot_do(cuda):
     model = synth.build_model(0).to("cuda:0")
     model.train()
