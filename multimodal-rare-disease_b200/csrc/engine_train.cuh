@@ -149,20 +149,14 @@ int train_ensure_packs(mrd_ctx* c, cudaStream_t s) {
         MRD_TRY(walloc(c, &w.o_t, 1LL * Hd * Hd));
         MRD_TRY(walloc(c, &w.f1_t, 1LL * Hd * F));
         MRD_TRY(walloc(c, &w.f2_t, 1LL * Hd * F));
-        const RawTensor *wq, *wk, *wv, *wo, *w1, *w2;
-        MRD_TRY(raw_need(c, p + "attention.self.query.weight", &wq));
-        MRD_TRY(raw_need(c, p + "attention.self.key.weight", &wk));
-        MRD_TRY(raw_need(c, p + "attention.self.value.weight", &wv));
-        MRD_TRY(raw_need(c, p + "attention.output.dense.weight", &wo));
-        MRD_TRY(raw_need(c, p + "intermediate.dense.weight", &w1));
-        MRD_TRY(raw_need(c, p + "output.dense.weight", &w2));
-        // qkv_t: [Hd(in)][3*Hd(out)]; the query block carries the folded 1/sqrt(64) like the forward pack
-        TRK("train.pack", CAT_MEM, pack_linear_t(wq->p, Hd, Hd, 0.125f, w.qkv_t, 3LL * Hd, 0, s));
-        TRK("train.pack", CAT_MEM, pack_linear_t(wk->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, Hd, s));
-        TRK("train.pack", CAT_MEM, pack_linear_t(wv->p, Hd, Hd, 1.0f, w.qkv_t, 3LL * Hd, 2 * Hd, s));
-        TRK("train.pack", CAT_MEM, pack_linear_t(wo->p, Hd, Hd, 1.0f, w.o_t, Hd, 0, s));
-        TRK("train.pack", CAT_MEM, pack_linear_t(w1->p, F, Hd, 1.0f, w.f1_t, F, 0, s));     // W1 [F,Hd] -> [Hd][F]
-        TRK("train.pack", CAT_MEM, pack_linear_t(w2->p, Hd, F, 1.0f, w.f2_t, Hd, 0, s));    // W2 [Hd,F] -> [F][Hd]
+        // transposed ([in][out]) copies of the PACKED bf16 weights (the query block already carries the folded
+        // 1/sqrt(64)): word-wise transposes, two matrices per launch
+        const BertLayerW& W = c->layers[i];
+        TRK("train.pack", CAT_MEM, transpose_pad2_bf16(W.qkv.w, Hd, Hd, w.qkv_t, nullptr, 0, 0, nullptr, 3 * Hd, nullptr,
+                                                      3 * Hd, s));
+        TRK("train.pack", CAT_MEM, transpose_pad2_bf16(W.o.w, Hd, Hd, w.o_t, nullptr, 0, 0, nullptr, Hd, nullptr, Hd, s));
+        TRK("train.pack", CAT_MEM, transpose_pad2_bf16(W.f1.w, Hd, Hd, w.f1_t, nullptr, 0, 0, nullptr, F, nullptr, F, s));
+        TRK("train.pack", CAT_MEM, transpose_pad2_bf16(W.f2.w, F, F, w.f2_t, nullptr, 0, 0, nullptr, Hd, nullptr, Hd, s));
     }
     t->packs_valid = true;
     return 0;
@@ -641,11 +635,16 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     return 0;
 }
 
-// dW = dY^T X through the tcgen05 GEMM: stage both operands token-minor, fp32 result into `dst`.
+// dW = dY^T X through the tcgen05 GEMM: stage both operands token-minor (the bias gradient = column sums of dY
+// is taken by the same staging kernel), fp32 result into `dst`.  Either destination may be null.
 int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* dY, int n_out, const bf16* X, int n_in,
-                float* dst, cudaStream_t s) {
+                float* dst, float* bias_dst, cudaStream_t s) {
+    if (!dst) {
+        if (bias_dst) TRK("train.colsum", CAT_MEM, colsum_bf16(dY, n_out, t->Ta, n_out, c->t_nrows, 1.0f, bias_dst, s));
+        return 0;
+    }
     TRK("train.transpose", CAT_MEM, transpose_pad2_bf16(dY, n_out, n_out, t->At, X, n_in, n_in, t->Bt, t->Ta, c->t_nrows,
-                                                        t->Tp, s));
+                                                        t->Tp, s, bias_dst));
     return run_f32(c, "train.wgrad", plan, dst, n_in, s);
 }
 
@@ -760,12 +759,12 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
             TRK("train.dropout", CAT_MEM, dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_ffn, t->dz, Hd, s));
             dz = t->dz;
         }
-        if (float* gw = grad_of(gt, pre + "output.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_f2, dz, Hd, b.g, F, gw, s));
-        if (float* gb = grad_of(gt, pre + "output.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
+        MRD_TRY(train_wgrad(c, t, t->w_f2, dz, Hd, b.g, F, grad_of(gt, pre + "output.dense.weight"),
+                            grad_of(gt, pre + "output.dense.bias"), s));
         MRD_TRY(run(c, "train.dgrad", dz == t->dz ? p.d_g : p.d_g0, s));
         TRK("train.gelu_bwd", CAT_MEM, gelu_bwd_bf16(b.u, t->dbig, T, F, c->t_nrows, t->dbig, s));
-        if (float* gw = grad_of(gt, pre + "intermediate.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_f1, t->dbig, F, b.h1, Hd, gw, s));
-        if (float* gb = grad_of(gt, pre + "intermediate.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(t->dbig, F, T, F, c->t_nrows, 1.0f, gb, s));
+        MRD_TRY(train_wgrad(c, t, t->w_f1, t->dbig, F, b.h1, Hd, grad_of(gt, pre + "intermediate.dense.weight"),
+                            grad_of(gt, pre + "intermediate.dense.bias"), s));
         MRD_TRY(run(c, "train.dgrad", p.d_h1, s));   // dh1 = du W1 + d_s2
         // h1 = LN1(s1), s1 = x + drop(Wo ctx + bo)
         TRK("train.ln_bwd", CAT_MEM, ln_bwd_bf16(b.s1, t->dh1, Lw.ln1g, c->bert_ln_eps, T, Hd, c->t_nrows, t->d_s,
@@ -776,8 +775,8 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
             TRK("train.dropout", CAT_MEM, dropout_bf16(t->d_s, Hd, T, Hd, c->t_nrows, d_att, t->dz, Hd, s));
             dz = t->dz;
         }
-        if (float* gw = grad_of(gt, pre + "attention.output.dense.weight")) MRD_TRY(train_wgrad(c, t, t->w_o, dz, Hd, b.ctx, Hd, gw, s));
-        if (float* gb = grad_of(gt, pre + "attention.output.dense.bias")) TRK("train.colsum", CAT_MEM, colsum_bf16(dz, Hd, T, Hd, c->t_nrows, 1.0f, gb, s));
+        MRD_TRY(train_wgrad(c, t, t->w_o, dz, Hd, b.ctx, Hd, grad_of(gt, pre + "attention.output.dense.weight"),
+                            grad_of(gt, pre + "attention.output.dense.bias"), s));
         MRD_TRY(run(c, "train.dgrad", dz == t->dz ? p.d_ctx : p.d_ctx0, s));
         if (t->dkv_acc) cudaMemsetAsync(t->dkv_acc, 0, sizeof(float) * static_cast<size_t>(T) * 2 * Hd, s);
         TRK("train.attention_bwd", CAT_ATTN, attention_backward(b.qkv, b.ctx, t->dctx, c->t_bias, c->t_seq_off, B, S, c->bert_heads,
@@ -789,9 +788,15 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
         float* gq = grad_of(gt, pre + "attention.self.query.weight");
         float* gk = grad_of(gt, pre + "attention.self.key.weight");
         float* gv = grad_of(gt, pre + "attention.self.value.weight");
-        if (gq || gk || gv) {
-            cudaMemsetAsync(t->wq_scratch, 0, sizeof(float) * 3 * static_cast<size_t>(Hd) * Hd, s);
-            MRD_TRY(train_wgrad(c, t, t->w_qkv, t->dqkv, 3 * Hd, b.x, Hd, t->wq_scratch, s));
+        float* bq = grad_of(gt, pre + "attention.self.query.bias");
+        float* bk = grad_of(gt, pre + "attention.self.key.bias");
+        float* bv = grad_of(gt, pre + "attention.self.value.bias");
+        const bool want_w = gq || gk || gv, want_b = bq || bk || bv;
+        if (want_w || want_b) {
+            if (want_w) cudaMemsetAsync(t->wq_scratch, 0, sizeof(float) * 3 * static_cast<size_t>(Hd) * Hd, s);
+            if (want_b) cudaMemsetAsync(t->bq_scratch, 0, sizeof(float) * 3 * Hd, s);
+            MRD_TRY(train_wgrad(c, t, t->w_qkv, t->dqkv, 3 * Hd, b.x, Hd, want_w ? t->wq_scratch : nullptr,
+                                want_b ? t->bq_scratch : nullptr, s));
             const size_t blk = sizeof(float) * static_cast<size_t>(Hd) * Hd;
             if (gq) {
                 TRK("train.scale", CAT_MEM, scale_f32(t->wq_scratch, 1LL * Hd * Hd, 0.125f, s));
@@ -799,13 +804,6 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
             }
             if (gk) cudaMemcpyAsync(gk, t->wq_scratch + 1LL * Hd * Hd, blk, cudaMemcpyDeviceToDevice, s);
             if (gv) cudaMemcpyAsync(gv, t->wq_scratch + 2LL * Hd * Hd, blk, cudaMemcpyDeviceToDevice, s);
-        }
-        float* bq = grad_of(gt, pre + "attention.self.query.bias");
-        float* bk = grad_of(gt, pre + "attention.self.key.bias");
-        float* bv = grad_of(gt, pre + "attention.self.value.bias");
-        if (bq || bk || bv) {
-            cudaMemsetAsync(t->bq_scratch, 0, sizeof(float) * 3 * Hd, s);
-            TRK("train.colsum", CAT_MEM, colsum_bf16(t->dqkv, 3 * Hd, T, 3 * Hd, c->t_nrows, 1.0f, t->bq_scratch, s));
             if (bq) {
                 TRK("train.scale", CAT_MEM, scale_f32(t->bq_scratch, Hd, 0.125f, s));
                 cudaMemcpyAsync(bq, t->bq_scratch, sizeof(float) * Hd, cudaMemcpyDeviceToDevice, s);

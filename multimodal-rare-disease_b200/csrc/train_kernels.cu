@@ -320,11 +320,13 @@ struct TransposeJob {
     long long ldx;
     int width;
     bf16* y;
+    float* colsum;   // optional: colsum[c] += sum over the live rows of x[r][c] (bias gradient of a dY operand)
 };
 
 __global__ void __launch_bounds__(256)
 transpose_pad_kernel(TransposeJob j0, TransposeJob j1, int rows, const int* __restrict__ dyn_rows, int Kp) {
     __shared__ uint32_t tile[64][33];
+    __shared__ float csum[8][64];
     const TransposeJob job = blockIdx.z ? j1 : j0;
     if (dyn_rows) rows = min(rows, __ldg(dyn_rows));
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
@@ -333,6 +335,7 @@ transpose_pad_kernel(TransposeJob j0, TransposeJob j1, int rows, const int* __re
     if (dyn_rows && r0 >= ((rows + 63) & ~63)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = c0 + 2 * lane;
+    float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int rp = warp * 4 + i;          // row pair 0..31
@@ -344,8 +347,20 @@ transpose_pad_kernel(TransposeJob j0, TransposeJob j1, int rows, const int* __re
         }
         tile[2 * lane][rp] = (a & 0xffffu) | (b << 16);
         tile[2 * lane + 1][rp] = (a >> 16) | (b & 0xffff0000u);
+        s0 += __uint_as_float(a << 16) + __uint_as_float(b << 16);
+        s1 += __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+    }
+    if (job.colsum) {
+        csum[warp][2 * lane] = s0;
+        csum[warp][2 * lane + 1] = s1;
     }
     __syncthreads();
+    if (job.colsum && threadIdx.x < 64 && c0 + threadIdx.x < job.width) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += csum[w][threadIdx.x];
+        atomicAdd(job.colsum + c0 + threadIdx.x, t);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int cc = warp * 8 + i;          // output row (= input column) within the tile
@@ -717,10 +732,11 @@ int gelu_bwd_bf16(const bf16* u, const bf16* dg, int rows, int width, const int*
 
 int transpose_pad_bf16(const bf16* x, long long ldx, int rows, int width, const int* dyn_rows, bf16* y, int Kp,
                        cudaStream_t s) {
-    return transpose_pad2_bf16(x, ldx, width, y, nullptr, 0, 0, nullptr, rows, dyn_rows, Kp, s);
+    return transpose_pad2_bf16(x, ldx, width, y, nullptr, 0, 0, nullptr, rows, dyn_rows, Kp, s, nullptr);
 }
 int transpose_pad2_bf16(const bf16* x0, long long ldx0, int width0, bf16* y0, const bf16* x1, long long ldx1,
-                        int width1, bf16* y1, int rows, const int* dyn_rows, int Kp, cudaStream_t s) {
+                        int width1, bf16* y1, int rows, const int* dyn_rows, int Kp, cudaStream_t s,
+                        float* colsum0) {
     if (Kp <= 0 || width0 <= 0) return 0;
     if (Kp % 2 || width0 % 2 || width1 % 2 || ldx0 % 2 || ldx1 % 2) {
         set_last_error("transpose_pad_bf16: odd extent");
@@ -728,7 +744,7 @@ int transpose_pad2_bf16(const bf16* x0, long long ldx0, int width0, bf16* y0, co
     }
     const int wmax = width0 > width1 ? width0 : width1;
     dim3 grid((Kp + 63) / 64, (wmax + 63) / 64, x1 ? 2 : 1);
-    TransposeJob j0{x0, ldx0, width0, y0}, j1{x1, ldx1, width1, y1};
+    TransposeJob j0{x0, ldx0, width0, y0, colsum0}, j1{x1, ldx1, width1, y1, nullptr};
     transpose_pad_kernel<<<grid, 256, 0, s>>>(j0, j1, rows, dyn_rows, Kp);
     return check_launch("transpose_pad_bf16");
 }

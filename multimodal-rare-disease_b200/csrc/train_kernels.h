@@ -58,10 +58,11 @@ int gelu_bwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* dg, int rows, int
 // row count are zero-filled so stale rows of the token-packed buffers contribute nothing.
 int transpose_pad_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
                        __nv_bfloat16* y, int Kp, cudaStream_t s);
-// two operands (same rows / Kp) in one launch
+// two operands (same rows / Kp) in one launch; colsum0 (optional): colsum0[c] += sum_r x0[r][c] over the live
+// rows - the bias gradient of the dY operand, taken while the tile is in flight anyway
 int transpose_pad2_bf16(const __nv_bfloat16* x0, long long ldx0, int width0, __nv_bfloat16* y0,
                         const __nv_bfloat16* x1, long long ldx1, int width1, __nv_bfloat16* y1, int rows,
-                        const int* dyn_rows, int Kp, cudaStream_t s);
+                        const int* dyn_rows, int Kp, cudaStream_t s, float* colsum0 = nullptr);
 // out[c] += scale * sum_r x[r,c]   (bias gradients)
 int colsum_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
                 float scale, float* out, cudaStream_t s);
