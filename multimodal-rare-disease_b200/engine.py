@@ -47,6 +47,7 @@ class Engine:
                 "there is no CPU fallback - use the reference implementation on CPU")
         self.lib = _lib.load()
         self.device = device
+        self.train_serial = 0
         self._sigs: Dict[str, tuple] = {}
         self._dirty = set()
         self._keep: Dict[str, list] = {}
@@ -297,6 +298,7 @@ class Engine:
             raise ValueError(f"batch mismatch: {B} images vs {ids.shape[0]} token rows")
         logits = self._f32(B, num_classes)
         self._train_inputs = (images, ids, mask)   # the backward re-reads the ids
+        self.train_serial = getattr(self, "train_serial", 0) + 1
         if B:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.mrd_train_forward(

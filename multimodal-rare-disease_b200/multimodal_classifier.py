@@ -33,10 +33,17 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, images, input_ids, attention_mask, seed, named_shapes, ddp, *params):
         ctx.eng, ctx.named_shapes, ctx.ddp = eng, named_shapes, ddp
-        return eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
+        logits = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
+        ctx.serial = eng.train_serial
+        return logits
 
     @staticmethod
     def backward(ctx, dlogits):
+        if ctx.serial != ctx.eng.train_serial:
+            raise RuntimeError(
+                "backward through a train-mode forward whose saved activations were overwritten by a newer "
+                "train-mode forward of the same model: the B200 training step keeps ONE forward pending "
+                "(call backward before the next forward, as the reference's loops do)")
         grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
         if ctx.ddp[1]:
             # data parallel: every gradient of the step lives in one flat buffer -> one all-reduce

@@ -550,6 +550,17 @@ def test_train_mode_refuses_what_it_cannot_do(cuda):
     model = synth.build_model(0).to("cuda:0")
     model.train()
     images, ids, mask = synth.make_inputs(2, 16, 1, None, H=32, W=32)
+    # one forward may be pending: the backward of an overwritten forward fails loudly, gradient accumulation
+    # over micro-steps (forward, backward, forward, backward) works
+    a = model(images.cuda(), ids.cuda(), mask.cuda())["logits"].sum()
+    b = model(images.cuda(), ids.cuda(), mask.cuda())["logits"].sum()
+    with pytest.raises(RuntimeError, match="overwritten"):
+        a.backward()
+    b.backward()
+    g1 = model.classifier.classifier[6].bias.grad.clone()
+    model(images.cuda(), ids.cuda(), mask.cuda())["logits"].sum().backward()
+    assert torch.allclose(model.classifier.classifier[6].bias.grad, 2 * g1)   # d(sum logits)/d(bias) = batch size
+    model.zero_grad()
     model.cnn_encoder.backbone.layer4.requires_grad_(True)
     with pytest.raises(NotImplementedError, match="backbone"):
         model(images.cuda(), ids.cuda(), mask.cuda())
