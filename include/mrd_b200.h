@@ -126,6 +126,13 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
                   const float* bias, void* C, long long ldc, const void* residual,
                   long long ld_res, float* out_f32, long long ld_f32, int act, void* stream);
 
+/* out_f32[M,N] += A[M,K] * W[N,K]^T on the same tcgen05 kernel with split-K: 128x256 output tiles whose K loop is
+ * cut into work items (one per SM), fp32 partial sums added into out_f32 (which the caller ZEROES first) with
+ * red.global.add.v4.f32.  The weight gradients dW = dY^T X of the training step (few output tiles, K = tokens).
+ * dyn_k (optional, device int): live part of K; the operands must be zero between it and the next multiple of 64. */
+int mrd_gemm_splitk_f32(const void* A, long long lda, int M, int K, const void* W, int N, float* out_f32,
+                        long long ld_f32, const int* dyn_k, void* stream);
+
 /* Conv2d(k in {1,3}, stride in {1,2}, pad k/2, no bias) + folded BatchNorm + optional residual +
  * activation on NHWC bf16 (TV:143-163).  Wt: [Cout][k][k][Cin] bf16 with the BN scale folded in,
  * bias: f32 [Cout] = beta - mean*scale.  Cin % 64 == 0, Cout % 64 == 0.

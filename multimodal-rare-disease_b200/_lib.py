@@ -46,6 +46,7 @@ SIGNATURES = {
     "mrd_ctx_launch_count": (_ll, [_vp]),
     "mrd_ctx_device_bytes": (_ll, [_vp]),
     "mrd_gemm_bf16": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),
+    "mrd_gemm_splitk_f32": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _vp, _vp]),
     "mrd_conv2d_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "mrd_conv3x3_flat_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "mrd_stem_conv_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),

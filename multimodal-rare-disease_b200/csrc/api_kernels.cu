@@ -26,6 +26,15 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }
 
+int mrd_gemm_splitk_f32(const void* A, long long lda, int M, int K, const void* W, int N, float* out_f32,
+                        long long ld_f32, const int* dyn_k, void* stream) {
+    GemmLaunch g;
+    int rc = plan_gemm_splitk(&g, static_cast<const __nv_bfloat16*>(A), lda, M, K,
+                              static_cast<const __nv_bfloat16*>(W), N, out_f32, ld_f32, dyn_k);
+    if (rc) return rc;
+    return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
 int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void* Wt, int Cout,
                          int ksize, int stride, const float* bias, void* Y, const void* residual,
                          int act, int out_pad, void* stream) {

@@ -273,7 +273,9 @@ struct TrainCnn {
     float *ones = nullptr, *zeros = nullptr;     // [2048] identity BatchNorm for the packers / zero bias
     float* dummy_bias = nullptr;                 // [2048] bias output of the packers (always zero, unused)
     std::vector<Bottleneck> blocks;              // raw (un-folded) filters
-    float* stats = nullptr;                      // [sites][4][2048]: sum, sumsq, scale, shift
+    float* stats = nullptr;                      // [sites][4][2048]: sum, sumsq, (2 spare)
+    BnSite* site_table = nullptr;                // device: one entry per BatchNorm layer (running-stat update)
+    std::vector<BnSite> site_host;
     std::vector<std::string> bn_names;           // site -> "cnn_encoder.backbone....bnX"
     int B = 0, H = 0, W = 0;
     long long ws_epoch = -1;
@@ -379,6 +381,7 @@ int train_cnn_plan(mrd_ctx* c, int B, int H, int W) {
     p.final_act = x;
     p.final_hw = h * w;
     tc->plan = std::move(p);
+    tc->site_host.clear();   // row counts / buffer addresses of the running-stat table belong to this plan
     tc->B = B; tc->H = H; tc->W = W;
     tc->ws_epoch = c->cnn_ws_epoch;
     return 0;
@@ -403,19 +406,29 @@ int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int
     cudaError_t e = cudaMemsetAsync(tc->stats, 0, sizeof(float) * n_sites * 4 * 2048, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(bn stats)");
     size_t site = 0;
+    const bool fill_table = tc->site_host.empty();
+    if (fill_table) tc->site_host.assign(n_sites, BnSite());
     auto bn = [&](bf16* y, long long rows, int C, const bf16* identity, int relu) -> int {
         const std::string& nm = tc->bn_names[site];
         float* st = tc->stats + site * 4 * 2048;
-        ++site;
         const RawTensor *g, *b, *rm, *rv;
         MRD_TRY(raw_need(c, nm + ".weight", &g));
         MRD_TRY(raw_need(c, nm + ".bias", &b));
-        MRD_TRY(raw_need(c, nm + ".running_mean", &rm));
-        MRD_TRY(raw_need(c, nm + ".running_var", &rv));
+        if (fill_table) {
+            MRD_TRY(raw_need(c, nm + ".running_mean", &rm));
+            MRD_TRY(raw_need(c, nm + ".running_var", &rv));
+            BnSite& e = tc->site_host[site];
+            e.sum = st; e.sumsq = st + 2048;
+            e.running_mean = const_cast<float*>(rm->p);
+            e.running_var = const_cast<float*>(rv->p);
+            e.n = static_cast<float>(rows);
+            e.C = C;
+        }
+        ++site;
         TRK("train.bn_stats", CAT_MEM, bn_stats_bf16(y, rows, C, st, st + 2048, s));
-        TRK("train.bn_finalize", CAT_MEM, bn_finalize(st, st + 2048, rows, C, g->p, b->p, c->bn_eps, static_cast<float>(t->o.bn_momentum),
-                            const_cast<float*>(rm->p), const_cast<float*>(rv->p), st + 4096, st + 6144, s));
-        TRK("train.bn_apply", CAT_MEM, bn_apply_bf16(y, rows, C, st + 4096, st + 6144, identity, relu, s));
+        // scale / shift are derived from the sums inside the normalise pass; the running buffers of all layers
+        // are updated by one launch at the end of the backbone
+        TRK("train.bn_apply", CAT_MEM, bn_apply_stats_bf16(y, rows, C, st, st + 2048, g->p, b->p, c->bn_eps, identity, relu, s));
         return 0;
     };
     const CnnPlan& p = tc->plan;
@@ -457,6 +470,14 @@ int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int
         w = wo;
     }
     TRK("train.avgpool", CAT_MEM, global_avgpool(p.final_act, B, p.final_hw, c->feat_dim, c->b_pooled, pooled_f32, s));
+    if (fill_table) {
+        MRD_TRY(walloc(c, reinterpret_cast<char**>(&tc->site_table), static_cast<long long>(n_sites * sizeof(BnSite))));
+        cudaError_t ce = cudaMemcpyAsync(tc->site_table, tc->site_host.data(), n_sites * sizeof(BnSite),
+                                         cudaMemcpyHostToDevice, s);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpyAsync(bn site table)");
+    }
+    TRK("train.bn_running", CAT_MEM, bn_update_running(tc->site_table, static_cast<int>(n_sites), 2048,
+                                                      static_cast<float>(t->o.bn_momentum), s));
     return 0;
 }
 

@@ -606,6 +606,53 @@ __global__ void bn_apply_kernel(bf16* __restrict__ y, long long n8, int C, const
     }
 }
 
+// scale / shift of all C channels are derived once per block into shared memory (2*C floats), then applied
+__global__ void bn_apply_stats_kernel(bf16* __restrict__ y, long long n8, int C, const float* __restrict__ sum,
+                                      const float* __restrict__ sumsq, float inv_n, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, const bf16* __restrict__ identity,
+                                      int relu) {
+    extern __shared__ float ss[];   // [C] scale, [C] shift
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mean = __ldg(sum + c) * inv_n;
+        const float var = fmaxf(__ldg(sumsq + c) * inv_n - mean * mean, 0.0f);
+        const float sc = __ldg(gamma + c) * rsqrtf(var + eps);
+        ss[c] = sc;
+        ss[C + c] = __ldg(beta + c) - mean * sc;
+    }
+    __syncthreads();
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>((i * 8) % C);
+        float v[8];
+        unpack8(reinterpret_cast<const uint4*>(y)[i], v);
+        const float4 s0 = *reinterpret_cast<const float4*>(ss + c), s1 = *reinterpret_cast<const float4*>(ss + c + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(ss + C + c), h1 = *reinterpret_cast<const float4*>(ss + C + c + 4);
+        v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+        v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+        if (identity) {
+            float r[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(identity) + i), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        reinterpret_cast<uint4*>(y)[i] = pack8(v);
+    }
+}
+
+__global__ void bn_update_running_kernel(const BnSite* __restrict__ table, float momentum) {
+    const BnSite st = table[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= st.C) return;
+    const float mean = st.sum[c] / st.n;
+    const float var = fmaxf(st.sumsq[c] / st.n - mean * mean, 0.0f);
+    st.running_mean[c] = (1.0f - momentum) * st.running_mean[c] + momentum * mean;
+    st.running_var[c] = (1.0f - momentum) * st.running_var[c] + momentum * var * (st.n / fmaxf(st.n - 1.0f, 1.0f));
+}
+
 // ------------------------------------------------------------------ transposed weight pack
 __global__ void __launch_bounds__(256)
 pack_linear_t_kernel(const float* __restrict__ w, int rows, int cols, float scale, bf16* __restrict__ out,
@@ -810,7 +857,7 @@ int bn_stats_bf16(const bf16* y, long long rows, int C, float* sum, float* sumsq
         set_last_error("bn_stats_bf16: odd channel count");
         return -1;
     }
-    long long split = (rows + 511) / 512;
+    long long split = (rows + 127) / 128;   // 16 rows per warp: short serial loops, more CTAs in flight
     if (split > 148 * 8) split = 148 * 8;
     if (split < 1) split = 1;
     dim3 grid((C + 63) / 64, static_cast<unsigned>(split));
@@ -837,6 +884,33 @@ int bn_apply_bf16(bf16* y, long long rows, int C, const float* scale, const floa
     if (grid > 148u * 16u) grid = 148u * 16u;
     bn_apply_kernel<<<grid, 256, 0, s>>>(y, n8, C, scale, shift, identity, relu);
     return check_launch("bn_apply_bf16");
+}
+
+int bn_apply_stats_bf16(bf16* y, long long rows, int C, const float* sum, const float* sumsq, const float* gamma,
+                        const float* beta, float eps, const bf16* identity, int relu, cudaStream_t s) {
+    if (rows <= 0 || C <= 0) return 0;
+    if (C % 8) {
+        set_last_error("bn_apply_stats_bf16: C %% 8 != 0");
+        return -1;
+    }
+    const long long n8 = rows * C / 8;
+    if (C > 4096) {
+        set_last_error("bn_apply_stats_bf16: C > 4096");
+        return -1;
+    }
+    // every block first derives the C scale/shift pairs: keep the grid to a few blocks per SM
+    unsigned grid = nblk(n8, 256 * 4);
+    if (grid > 148u * 4u) grid = 148u * 4u;
+    if (grid < 1u) grid = 1u;
+    bn_apply_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(y, n8, C, sum, sumsq, 1.0f / static_cast<float>(rows),
+                                                                   gamma, beta, eps, identity, relu);
+    return check_launch("bn_apply_stats_bf16");
+}
+int bn_update_running(const BnSite* table, int sites, int max_C, float momentum, cudaStream_t s) {
+    if (sites <= 0) return 0;
+    dim3 grid((max_C + 127) / 128, sites);
+    bn_update_running_kernel<<<grid, 128, 0, s>>>(table, momentum);
+    return check_launch("bn_update_running");
 }
 
 int pack_linear_t(const float* w, int rows, int cols, float scale, bf16* out, long long ld_out, int col_off,

@@ -112,6 +112,22 @@ int bn_finalize(const float* sum, const float* sumsq, long long n, int C, const 
 // y = act(y*scale[c] + shift[c] (+ identity)) in place on [rows, C] bf16; C % 8 == 0.
 int bn_apply_bf16(__nv_bfloat16* y, long long rows, int C, const float* scale, const float* shift,
                   const __nv_bfloat16* identity, int relu, cudaStream_t s);
+// The same with scale / shift derived on the fly from the batch sums (no separate finalize launch):
+// mean = sum/n, var = sumsq/n - mean^2, scale = gamma*rsqrt(var+eps), shift = beta - mean*scale.
+int bn_apply_stats_bf16(__nv_bfloat16* y, long long rows, int C, const float* sum, const float* sumsq,
+                        const float* gamma, const float* beta, float eps, const __nv_bfloat16* identity, int relu,
+                        cudaStream_t s);
+// Running-statistics update of every BatchNorm layer of a forward in ONE launch (what nn.BatchNorm2d does in
+// train mode: running <- (1-m)*running + m*(mean, var*n/(n-1))).  table: device array, one entry per layer.
+struct BnSite {
+    const float* sum;
+    const float* sumsq;
+    float* running_mean;
+    float* running_var;
+    float n;
+    int C;
+};
+int bn_update_running(const BnSite* table, int sites, int max_C, float momentum, cudaStream_t s);
 
 // w [rows, cols] fp32 -> out[c][col_off + r] = bf16(w[r][c] * scale), out row stride ld_out: the
 // transposed (input-major) copy of an nn.Linear weight used as the B operand of dX = dY W.

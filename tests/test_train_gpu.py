@@ -130,6 +130,36 @@ def test_attention_backward_packed_layout(cuda, lib):
     assert torch.equal(d_pack, d_dense[rows])
 
 
+@pytest.mark.parametrize("M,N,K,live", [(768, 3072, 2048, None), (3072, 768, 4096, 2560), (2304, 768, 1024, 700),
+                                        (768, 768, 512, 64), (256, 64, 8192, None)])
+def test_splitk_weight_gradient_gemm(cuda, lib, M, N, K, live):
+    """dW = dY^T X: split-K tcgen05 GEMM with fp32 partial sums reduced in L2, bounded by the live K on the device."""
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(M, K, generator=g).to(cuda, torch.bfloat16)
+    W = torch.randn(N, K, generator=g).to(cuda, torch.bfloat16)
+    dyn = None
+    if live is not None:
+        up = (live + 63) // 64 * 64
+        A[:, live:up] = 0          # the staging transposes zero-fill up to the next K block ...
+        W[:, live:up] = 0
+        A[:, up:] = float("nan")   # ... and nothing beyond it may be read
+        W[:, up:] = float("nan")
+        dyn = torch.tensor([live], dtype=torch.int32, device=cuda)
+    out = torch.zeros(M, N, device=cuda)
+    assert lib.mrd_gemm_splitk_f32(_p(A), K, M, K, _p(W), N, _p(out), N, None if dyn is None else _p(dyn),
+                                   _stream()) == 0, lib.mrd_last_error()
+    kk = K if live is None else live
+    ref = A[:, :kk].float() @ W[:, :kk].float().T
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert ((out - ref).norm() / ref.norm()).item() <= 3e-5   # bf16 products are exact in fp32; only the order differs
+    # accumulation semantics: a second launch adds on top
+    assert lib.mrd_gemm_splitk_f32(_p(A), K, M, K, _p(W), N, _p(out), N, None if dyn is None else _p(dyn),
+                                   _stream()) == 0
+    torch.cuda.synchronize()
+    assert ((out - 2 * ref).norm() / ref.norm()).item() <= 6e-5
+
+
 @pytest.mark.parametrize("width", [768, 512])
 def test_layernorm_backward_vs_autograd(cuda, lib, width):
     rows = 1000
