@@ -78,7 +78,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 // one binary serves the compute-bound GEMMs (deep operand pipeline, no residual ring) and the
 // memory-bound short-K convolutions with residual (shallow operand pipeline, deep residual ring)):
 //   [stages x A_STAGE][stages x B_STAGE][2 x 16 KB store staging][ring x 16 KB residual][barriers]
-template <int BLOCK_N, int MODE>
+// SPLITK (generic mode only) is a separate instantiation so that the forward's kernels compile exactly as they
+// did before split-K existed: measured, the merged version cost the forward 3 % (different epilogue schedule).
+template <int BLOCK_N, int MODE, bool SPLITK = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BLOCK_N, MODE>;
@@ -153,10 +155,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
     constexpr int NSUB = BLOCK_N / 64;
     int num_k = p.num_taps * p.kc_per_tap;
-    if (p.dyn_k) {   // token-packed contraction (weight gradients): only the live K blocks
-        int live_k = (__ldg(p.dyn_k) + C::BLOCK_K - 1) / C::BLOCK_K;
-        live_k = live_k < 1 ? 1 : live_k;
-        num_k = live_k < num_k ? live_k : num_k;
+    if constexpr (SPLITK) {
+        if (p.dyn_k) {   // token-packed contraction (weight gradients): only the live K blocks
+            int live_k = (__ldg(p.dyn_k) + C::BLOCK_K - 1) / C::BLOCK_K;
+            live_k = live_k < 1 ? 1 : live_k;
+            num_k = live_k < num_k ? live_k : num_k;
+        }
     }
     const int box_rows = p.tw * p.th * p.nb;
     const uint32_t a_box_bytes = static_cast<uint32_t>(box_rows) * C::ROW_BYTES;
@@ -170,9 +174,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     // split-K: work item = (output tile, K slice); item i covers tile i % total_tiles, slice i / total_tiles.
     // ksplit == 1 (every launch of the forward) makes items and tiles the same thing.
-    int ksplit = p.ksplit > 1 ? p.ksplit : 1;
-    ksplit = ksplit < num_k ? ksplit : num_k;
-    const int total_items = total_tiles * ksplit;
+    int ksplit = 1;
+    if constexpr (SPLITK) {
+        ksplit = p.ksplit > 1 ? p.ksplit : 1;
+        ksplit = ksplit < num_k ? ksplit : num_k;
+    }
+    const int total_items = SPLITK ? total_tiles * ksplit : total_tiles;
     const int my_tiles = total_items > bid ? (total_items - bid + nblk - 1) / nblk : 0;
 
     if (warp == 0 && WRES) {
@@ -302,9 +309,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int stage = 0;
         uint32_t phase = 0;
         for (int item = bid; item < total_items; item += nblk) {
-            const int split = item / total_tiles;
-            const TileCoord t = decode_tile(p, item - split * total_tiles);
-            const int k_begin = split * num_k / ksplit, k_end = (split + 1) * num_k / ksplit;
+            const int split = SPLITK ? item / total_tiles : 0;
+            const TileCoord t = decode_tile(p, SPLITK ? item - split * total_tiles : item);
+            const int k_begin = SPLITK ? split * num_k / ksplit : 0;
+            const int k_end = SPLITK ? (split + 1) * num_k / ksplit : num_k;
             for (int ks = k_begin; ks < k_end; ++ks) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
@@ -335,8 +343,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            const int split = item / total_tiles;
-            const int k_begin = split * num_k / ksplit, k_end = (split + 1) * num_k / ksplit;
+            const int split = SPLITK ? item / total_tiles : 0;
+            const int k_begin = SPLITK ? split * num_k / ksplit : 0;
+            const int k_end = SPLITK ? (split + 1) * num_k / ksplit : num_k;
             for (int ks = k_begin; ks < k_end; ++ks) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
@@ -367,7 +376,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             int slot = 0;
             uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                const TileCoord t = decode_tile(p, (bid + it * nblk) % total_tiles);
+                const TileCoord t = decode_tile(p, SPLITK ? (bid + it * nblk) % total_tiles : bid + it * nblk);
                 for (int sub = 0; sub < NSUB; ++sub) {
                     mbar_wait(rempty_bar(slot), phase ^ 1u);
                     if (lane == 0) {
@@ -394,13 +403,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int rslot = 0;
         uint32_t rphase = 0;
 
-        TileCoord t = decode_tile(p, total_tiles > 0 ? bid % total_tiles : 0);
+        TileCoord t = decode_tile(p, SPLITK ? (total_tiles > 0 ? bid % total_tiles : 0) : bid);
         for (int q = 0; q < nq; ++q) {
             const int sub = q % NSUB;
             const int it = q / NSUB;
             const int acc = it & 1;
             const uint32_t buf = q & 1u;
-            if (sub == 0) t = decode_tile(p, (bid + it * nblk) % total_tiles);
+            if (sub == 0) t = decode_tile(p, SPLITK ? (bid + it * nblk) % total_tiles : bid + it * nblk);
             const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;  // first global column of this thread
 
             if (sub == 0) {
@@ -460,7 +469,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     const long long pix =
                         (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
                     float* f32_row = p.out_f32 + pix * p.ld_f32 + col0;
-                    if (p.f32_accum) {   // split-K partial result: reduce in L2
+                    if constexpr (SPLITK) {   // split-K partial result: reduce in L2
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             atomicAdd(reinterpret_cast<float4*>(f32_row + j),
@@ -510,11 +519,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool SPLITK = false>
 int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
-    auto kfn = conv_gemm_kernel<BLOCK_N, MODE>;
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK>;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -1029,6 +1038,13 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
         }
         set_last_error("launch_gemm: bad flat3 block_n %d", g->block_n);
         return -1;
+    }
+    if (g->p.f32_accum) {   // plan_gemm_splitk
+        switch (g->block_n) {
+            case 64: return launch_variant<64, MODE_GENERIC, true>(g, stream, sm_limit);
+            case 128: return launch_variant<128, MODE_GENERIC, true>(g, stream, sm_limit);
+            case 256: return launch_variant<256, MODE_GENERIC, true>(g, stream, sm_limit);
+        }
     }
     switch (g->block_n) {
         case 64: return launch_variant<64, MODE_GENERIC>(g, stream, sm_limit);
