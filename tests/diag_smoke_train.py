@@ -2,7 +2,7 @@
 """Diagnostic for the smoke() training check: per-group gradient error of the linear-loss step on the sensitised
 weights, for several image sizes / with and without a preceding eval forward."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn as nn
 import synth

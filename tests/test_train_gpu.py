@@ -297,7 +297,7 @@ def test_train_step_vs_reference_fixture(cuda, sens):
         report.append((err, k, g.norm().item() / ref["norm"]))
     report.sort(reverse=True)
     print("worst gradients vs the reference fixture (rel err, name, norm ratio):", report[:4])
-    # random-init BERT is an ill-conditioned case for ANY bf16 step (tools/diag_train_noise.py: stock PyTorch
+    # random-init BERT is an ill-conditioned case for ANY bf16 step (tests/diag_train_noise.py: stock PyTorch
     # bf16 autocast of the same model is 16-25 % off fp32 on the query/key gradients), so the per-tensor bar is
     # the bf16-autocast oracle's own error on this very case, not a fixed 5 %.
     _, g32 = _oracle_grads_gpu(sens, images, ids, mask, labels=torch.tensor(fix["labels"]))
