@@ -326,7 +326,10 @@ def main():
                     "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["src"] + " (sustained: timed inside a long step)",
                     "launches_per_step": n_l, "avg_launch_ms": t_ms / max(n_l, 1),
                     "flops_per_launch_avg": t_fl / max(n_l, 1), "share_of_step": t_ms / all_ms if all_ms else None,
-                    "traffic": _ncu_traffic(),
+                    # DRAM bytes per launch of this kernel family (dram__bytes_read.sum + dram__bytes_write.sum, ncu);
+                    # the capture it comes from is described in traffic_detail
+                    "traffic": (_ncu_traffic() or {}).get("dram_bytes_per_launch"),
+                    "traffic_detail": _ncu_traffic(),
                     "note": "achieved counts ALGORITHMIC flops (dense, as the reference executes; SURVEY 8(d)). "
                             f"The BERT launches skip padded tokens (live fraction {live_frac:.3f} of B*S) and the last "
                             "layer's post-attention half runs on CLS rows only, so executed FLOP/s are lower: "
