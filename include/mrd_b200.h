@@ -257,6 +257,27 @@ int mrd_attention_bwd_bf16(const void* qkv, const void* ctx, const void* dctx, c
 int mrd_layernorm_bwd_bf16(const void* s_in, const void* dy, const float* gamma, float eps, int rows,
                            int width, void* dx, float* dgamma, float* dbeta, void* stream);
 
+/* clip_grad_norm_(parameters, max_norm) + torch.optim.AdamW.step() of the reference's loop (src/train.py:307-320,
+ * :193-198) as two multi-tensor launches without a host synchronisation: the global L2 norm of all gradients is
+ * reduced into sqnorm_dev[0] (its square; zeroed inside), the clip coefficient min(1, max_norm / (norm + 1e-6)) is
+ * derived on the device (max_norm <= 0: no clipping) and applied to the gradient as it is read (the gradient
+ * tensors themselves are NOT rescaled).  Decoupled weight decay, bias correction with the common `step` (1-based)
+ * exactly as torch.optim.AdamW (amsgrad = False).  All arrays are DEVICE arrays: tensors_dev[n_tensors] (g may be
+ * NULL: parameter skipped), and a chunk table - chunk c covers elements [chunk_off_dev[c], + chunk_elems) of tensor
+ * chunk_tensor_dev[c]; chunk_elems % 4 == 0. */
+typedef struct {
+    float* p;        /* parameter, updated in place */
+    const float* g;  /* gradient */
+    float* m;        /* exp_avg */
+    float* v;        /* exp_avg_sq */
+    long long n;     /* elements */
+    float lr;
+    float wd;
+} mrd_adamw_tensor;
+int mrd_adamw_step(const mrd_adamw_tensor* tensors_dev, int n_tensors, const int* chunk_tensor_dev,
+                   const long long* chunk_off_dev, int n_chunks, int chunk_elems, float beta1, float beta2,
+                   float eps, long long step, float max_norm, float* sqnorm_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ from .fusion_model import AttentionFusion, CrossModalAttention, MultimodalFusion
 from .multimodal_classifier import (ClassificationHead, ImageOnlyClassifier, MultimodalClassifier,
                                     TextOnlyClassifier, create_baseline_classifiers,
                                     create_multimodal_classifier)
+from .optim import FusedAdamW
 from .parallel import DataParallelForward, allreduce_mean_, shard_bounds
 from ._lib import MrdError
 

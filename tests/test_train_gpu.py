@@ -576,6 +576,46 @@ def test_reference_amp_loop_shape_works(cuda, sens):
     assert (num / den) ** 0.5 <= 2e-2, (num / den) ** 0.5
 
 
+def test_fused_adamw_matches_torch(cuda):
+    """mrd_b200.FusedAdamW(max_grad_norm=1) == clip_grad_norm_(1) + torch.optim.AdamW, per-group lr / weight decay,
+    a parameter without gradient, interchangeable state_dict."""
+    import mrd_b200
+
+    g = torch.Generator().manual_seed(21)
+    shapes = [(768, 768), (3072,), (10, 128), (7,), (300, 33)]
+
+    def make():
+        return [nn.Parameter(torch.randn(*s, generator=g.manual_seed(21 + i)).cuda()) for i, s in enumerate(shapes)]
+
+    a, b = make(), make()
+    groups = lambda ps: [{"params": ps[:2], "lr": 5e-5}, {"params": ps[2:], "lr": 1e-3, "weight_decay": 0.0}]
+    ref = torch.optim.AdamW(groups(a), lr=1e-4, weight_decay=0.05)
+    mine = mrd_b200.FusedAdamW(groups(b), lr=1e-4, weight_decay=0.05, max_grad_norm=1.0)
+    for step in range(4):
+        gg = torch.Generator().manual_seed(100 + step)
+        for i, (p, q) in enumerate(zip(a, b)):
+            if i == 3:      # never receives a gradient: untouched by both (no weight decay either)
+                continue
+            grad = (torch.randn(p.shape, generator=gg) * (3.0 if step % 2 else 1e-5)).cuda()   # clipped / not clipped
+            p.grad, q.grad = grad.clone(), grad.clone()
+        total = nn.utils.clip_grad_norm_(a, 1.0)
+        ref.step()
+        mine.step()
+        assert abs(mine.last_grad_norm.item() - total.item()) <= 1e-5 * total.item()
+    torch.cuda.synchronize()
+    for i, (p, q) in enumerate(zip(a, b)):
+        assert ((p - q).norm() / p.norm()).item() <= 1e-6, i
+        if i != 3:
+            assert torch.allclose(ref.state[p]["exp_avg"], mine.state[q]["exp_avg"], rtol=1e-5, atol=1e-9)
+            assert torch.allclose(ref.state[p]["exp_avg_sq"], mine.state[q]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+            assert int(mine.state[q]["step"]) == 4
+    assert torch.equal(a[3], b[3])
+    # checkpoints are interchangeable with torch.optim.AdamW (src/train.py:394-437 saves optimizer_state_dict)
+    other = mrd_b200.FusedAdamW(groups(make()), lr=1e-4, weight_decay=0.05)
+    other.load_state_dict(ref.state_dict())
+    assert other.param_groups[1]["lr"] == 1e-3
+
+
 def test_train_mode_refuses_what_it_cannot_do(cuda):
     model = synth.build_model(0).to("cuda:0")
     model.train()

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--seq", type=int, default=128)
     ap.add_argument("--bn-eval", action="store_true", help="frozen backbone in eval mode (running statistics)")
     ap.add_argument("--fused-adamw", action="store_true", help="torch.optim.AdamW(fused=True)")
+    ap.add_argument("--native-adamw", action="store_true",
+                    help="mrd_b200.FusedAdamW(max_grad_norm=1): clip + AdamW in two library launches")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
     import torch
@@ -63,14 +65,20 @@ def main():
     ids[:, 0] = 101
     ids, mask = ids.to(dev), mask.to(dev)
     labels = torch.randint(0, 10, (B,), generator=g).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.05, fused=args.fused_adamw or None)
+    if args.native_adamw:
+        import mrd_b200
+
+        opt = mrd_b200.FusedAdamW(model.parameters(), lr=5e-5, weight_decay=0.05, max_grad_norm=1.0)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.05, fused=args.fused_adamw or None)
     crit = nn.CrossEntropyLoss()
 
     def step():
         opt.zero_grad(set_to_none=True)
         loss = crit(model(images, ids, mask)["logits"], labels)
         loss.backward()
-        nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if not args.native_adamw:
+            nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
 
@@ -126,6 +134,8 @@ def main():
                 "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "per_gpu_batch": B, "seq_len": S, "dtype": "bf16 (fp32 master weights, fp32 grads)",
                 "bn": "running statistics" if args.bn_eval else "batch statistics",
+                "optimizer": "mrd_b200.FusedAdamW (clip fused)" if args.native_adamw else
+                             ("torch AdamW fused" if args.fused_adamw else "torch AdamW (foreach) + clip_grad_norm_"),
                 "library_kernel_ms_profiled_step": round(tot, 3), "library_launches_per_step": launches // args.steps,
                 "loss_first_last": [losses[0] if losses else None, loss.item()], "live_token_fraction": live,
                 "trainable_params": sum(p.numel() for p in model.parameters() if p.requires_grad),
