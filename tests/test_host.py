@@ -190,3 +190,22 @@ def test_gradient_bucket_allreduce_world2():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] for r in res)
     assert mrd_b200.allreduce_mean_(torch.ones(3)) is not None   # no process group: a no-op
+
+
+def test_fused_adamw_host_contract():
+    """FusedAdamW is a torch.optim.Optimizer with AdamW's param-group / state_dict layout; it has no CPU path."""
+    lin = torch.nn.Linear(4, 3)
+    groups = [{"params": [lin.weight], "lr": 1e-3}, {"params": [lin.bias], "lr": 1e-2, "weight_decay": 0.0}]
+    opt = mrd_b200.FusedAdamW(groups, lr=5e-5, weight_decay=0.05, max_grad_norm=1.0)
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert opt.param_groups[0]["weight_decay"] == 0.05 and opt.param_groups[1]["weight_decay"] == 0.0
+    ref = torch.optim.AdamW([{"params": [lin.weight], "lr": 1e-3}, {"params": [lin.bias], "lr": 1e-2, "weight_decay": 0.0}],
+                            lr=5e-5, weight_decay=0.05)
+    lin(torch.randn(2, 4)).sum().backward()
+    ref.step()
+    opt.load_state_dict(ref.state_dict())          # a torch AdamW checkpoint loads
+    assert set(opt.state_dict()["state"][0]) >= {"step", "exp_avg", "exp_avg_sq"}
+    with pytest.raises(mrd_b200.MrdError, match="CUDA"):
+        opt.step()
+    with pytest.raises(ValueError):
+        mrd_b200.FusedAdamW([lin.weight], lr=-1.0)
