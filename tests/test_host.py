@@ -209,3 +209,45 @@ def test_fused_adamw_host_contract():
         opt.step()
     with pytest.raises(ValueError):
         mrd_b200.FusedAdamW([lin.weight], lr=-1.0)
+
+
+def test_predict_batch_formatting_matches_reference_semantics():
+    """format_predictions == the per-sample dicts of MultimodalPredictor.predict_batch (src/predict.py:241-267),
+    including numpy's argsort()[::-1] tie order; predict_batch_tensors drives a model object through it."""
+    import numpy as np
+
+    probs = torch.tensor([[0.1, 0.5, 0.2, 0.2], [0.25, 0.25, 0.25, 0.25], [0.7, 0.1, 0.1, 0.1]])
+    names = ["A", "B", "C"]          # shorter than the class count: the reference falls back to Class_i
+    got = mrd_b200.format_predictions(probs, names, top_k=3)
+    for i, sample in enumerate(probs.numpy()):
+        top = sample.argsort()[::-1][:3]
+        want = [{"syndrome": names[j] if j < len(names) else f"Class_{j}", "class_id": int(j),
+                 "confidence": float(sample[j])} for j in top]
+        assert got[i]["sample_idx"] == i and got[i]["predictions"] == want and got[i]["top_prediction"] == want[0]
+    assert mrd_b200.format_predictions(probs, None, top_k=0)[0]["top_prediction"] is None
+
+    class Fake:
+        training = True
+        calls = []
+
+        def eval(self):
+            self.training = False
+
+        def train(self, mode=True):
+            self.training = mode
+
+        def forward_host(self, images, ids, mask, micro_batch=512):
+            self.calls.append(("host", micro_batch, self.training))
+            return {"probs": probs[: images.shape[0]]}
+
+        def __call__(self, images, input_ids, attention_mask):
+            self.calls.append(("dev", self.training))
+            return {"probs": probs[: images.shape[0]]}
+
+    m = Fake()
+    res = mrd_b200.predict_batch_tensors(m, torch.zeros(2, 3, 8, 8), torch.zeros(2, 4, dtype=torch.long), None,
+                                         names, top_k=1, micro_batch=64)
+    assert m.calls == [("host", 64, False)] and m.training is True and len(res) == 2
+    assert res[1]["top_prediction"]["class_id"] == int(np.argsort(probs[1].numpy())[::-1][0])
+    with pytest.raises(ValueError, match="must match"):
+        mrd_b200.predict_batch_tensors(m, torch.zeros(2, 3, 8, 8), torch.zeros(3, 4, dtype=torch.long), None)

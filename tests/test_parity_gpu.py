@@ -297,3 +297,21 @@ def test_all_hidden_states_vs_oracle(cuda, state):
     # intermediate layers differ from their neighbours (really per-layer, not copies)
     assert not torch.equal(states[5], states[6])
 
+
+
+def test_predict_batch_tensors_host_and_device(cuda, state):
+    """SURVEY 8(f).4 glue: host-resident tensors through forward_host, formatted like
+    MultimodalPredictor.predict_batch (src/predict.py:199-269); same rows as the device path."""
+    model = _use(state, "sens")
+    images, ids, mask = synth.make_inputs(7, 48, 93, [48, 20, 1, 33, 48, 7, 40])
+    names = [f"syndrome_{i}" for i in range(10)]
+    host = mrd_b200.predict_batch_tensors(model, images.pin_memory(), ids.pin_memory(), mask.pin_memory(), names,
+                                          top_k=3, micro_batch=3)
+    dev = mrd_b200.predict_batch_tensors(model, images.cuda(), ids.cuda(), mask.cuda(), names, top_k=3)
+    assert host == dev and len(host) == 7 and not model.training
+    probs = _fwd(model, images, ids, mask)["probs"].cpu()
+    for i, r in enumerate(host):
+        assert r["sample_idx"] == i and len(r["predictions"]) == 3
+        assert r["top_prediction"]["class_id"] == int(probs[i].argmax())
+        assert r["top_prediction"]["syndrome"] == names[r["top_prediction"]["class_id"]]
+        assert abs(r["top_prediction"]["confidence"] - probs[i].max().item()) < 1e-6
