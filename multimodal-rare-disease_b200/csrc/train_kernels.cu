@@ -411,11 +411,6 @@ __global__ void scale_f32_kernel(float* __restrict__ x, long long n, float a) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) x[i] *= a;
 }
-__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
-                               float* __restrict__ out) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = a[i] + b[i];
-}
 __global__ void relu_bwd_f32_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n,
                                     float* __restrict__ dx) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -565,47 +560,6 @@ bn_stats_kernel(const bf16* __restrict__ y, long long rows, int C, float* __rest
     }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float n, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ scale,
-                                   float* __restrict__ shift) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float mean = sum[c] / n;
-    const float var = fmaxf(sumsq[c] / n - mean * mean, 0.0f);
-    const float sc = gamma[c] * rsqrtf(var + eps);
-    scale[c] = sc;
-    shift[c] = beta[c] - mean * sc;
-    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
-    if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * (n / fmaxf(n - 1.0f, 1.0f));
-}
-
-__global__ void bn_apply_kernel(bf16* __restrict__ y, long long n8, int C, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const bf16* __restrict__ identity, int relu) {
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>((i * 8) % C);
-        float v[8];
-        unpack8(reinterpret_cast<const uint4*>(y)[i], v);
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
-        const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-        v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-        v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-        if (identity) {
-            float r[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(identity) + i), r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r[j];
-        }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        reinterpret_cast<uint4*>(y)[i] = pack8(v);
-    }
-}
-
 // scale / shift of all C channels are derived once per block into shared memory (2*C floats), then applied
 __global__ void bn_apply_stats_kernel(bf16* __restrict__ y, long long n8, int C, const float* __restrict__ sum,
                                       const float* __restrict__ sumsq, float inv_n, const float* __restrict__ gamma,
@@ -651,24 +605,6 @@ __global__ void bn_update_running_kernel(const BnSite* __restrict__ table, float
     const float var = fmaxf(st.sumsq[c] / st.n - mean * mean, 0.0f);
     st.running_mean[c] = (1.0f - momentum) * st.running_mean[c] + momentum * mean;
     st.running_var[c] = (1.0f - momentum) * st.running_var[c] + momentum * var * (st.n / fmaxf(st.n - 1.0f, 1.0f));
-}
-
-// ------------------------------------------------------------------ transposed weight pack
-__global__ void __launch_bounds__(256)
-pack_linear_t_kernel(const float* __restrict__ w, int rows, int cols, float scale, bf16* __restrict__ out,
-                     long long ld_out, int col_off) {
-    __shared__ float tile[32][33];
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < rows && c < cols) ? w[static_cast<long long>(r) * cols + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + tx;
-        if (c < cols && r < rows) out[static_cast<long long>(c) * ld_out + col_off + r] = __float2bfloat16(tile[tx][i] * scale);
-    }
 }
 
 }  // namespace
@@ -777,10 +713,6 @@ int gelu_bwd_bf16(const bf16* u, const bf16* dg, int rows, int width, const int*
     return check_launch("gelu_bwd_bf16");
 }
 
-int transpose_pad_bf16(const bf16* x, long long ldx, int rows, int width, const int* dyn_rows, bf16* y, int Kp,
-                       cudaStream_t s) {
-    return transpose_pad2_bf16(x, ldx, width, y, nullptr, 0, 0, nullptr, rows, dyn_rows, Kp, s, nullptr);
-}
 int transpose_pad2_bf16(const bf16* x0, long long ldx0, int width0, bf16* y0, const bf16* x1, long long ldx1,
                         int width1, bf16* y1, int rows, const int* dyn_rows, int Kp, cudaStream_t s,
                         float* colsum0) {
@@ -818,11 +750,6 @@ int scale_f32(float* x, long long n, float a, cudaStream_t s) {
     if (n <= 0) return 0;
     scale_f32_kernel<<<nblk(n, 256), 256, 0, s>>>(x, n, a);
     return check_launch("scale_f32");
-}
-int add_f32(const float* a, const float* b, long long n, float* out, cudaStream_t s) {
-    if (n <= 0) return 0;
-    add_f32_kernel<<<nblk(n, 256), 256, 0, s>>>(a, b, n, out);
-    return check_launch("add_f32");
 }
 int relu_bwd_f32(const float* y, const float* dy, long long n, float* dx, cudaStream_t s) {
     if (n <= 0) return 0;
@@ -864,28 +791,6 @@ int bn_stats_bf16(const bf16* y, long long rows, int C, float* sum, float* sumsq
     bn_stats_kernel<<<grid, 256, 0, s>>>(y, rows, C, sum, sumsq);
     return check_launch("bn_stats_bf16");
 }
-int bn_finalize(const float* sum, const float* sumsq, long long n, int C, const float* gamma, const float* beta,
-                float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                cudaStream_t s) {
-    if (C <= 0) return 0;
-    bn_finalize_kernel<<<nblk(C, 128), 128, 0, s>>>(sum, sumsq, static_cast<float>(n), C, gamma, beta, eps, momentum,
-                                                  running_mean, running_var, scale, shift);
-    return check_launch("bn_finalize");
-}
-int bn_apply_bf16(bf16* y, long long rows, int C, const float* scale, const float* shift, const bf16* identity,
-                  int relu, cudaStream_t s) {
-    if (rows <= 0 || C <= 0) return 0;
-    if (C % 8) {
-        set_last_error("bn_apply_bf16: C %% 8 != 0");
-        return -1;
-    }
-    const long long n8 = rows * C / 8;
-    unsigned grid = nblk(n8, 256);
-    if (grid > 148u * 16u) grid = 148u * 16u;
-    bn_apply_kernel<<<grid, 256, 0, s>>>(y, n8, C, scale, shift, identity, relu);
-    return check_launch("bn_apply_bf16");
-}
-
 int bn_apply_stats_bf16(bf16* y, long long rows, int C, const float* sum, const float* sumsq, const float* gamma,
                         const float* beta, float eps, const bf16* identity, int relu, cudaStream_t s) {
     if (rows <= 0 || C <= 0) return 0;
@@ -911,14 +816,6 @@ int bn_update_running(const BnSite* table, int sites, int max_C, float momentum,
     dim3 grid((max_C + 127) / 128, sites);
     bn_update_running_kernel<<<grid, 128, 0, s>>>(table, momentum);
     return check_launch("bn_update_running");
-}
-
-int pack_linear_t(const float* w, int rows, int cols, float scale, bf16* out, long long ld_out, int col_off,
-                  cudaStream_t s) {
-    if (rows <= 0 || cols <= 0) return 0;
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-    pack_linear_t_kernel<<<grid, 256, 0, s>>>(w, rows, cols, scale, out, ld_out, col_off);
-    return check_launch("pack_linear_t");
 }
 
 }  // namespace mrd

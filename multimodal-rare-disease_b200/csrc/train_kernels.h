@@ -56,9 +56,7 @@ int gelu_bwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* dg, int rows, int
 // y[c][r] = r < live ? x[r][c] : 0 for r < Kp; x: [rows, width] bf16 (row stride ldx), y: [width][Kp].
 // dW = dY^T X contracts over tokens, so both operands are needed token-minor; columns beyond the live
 // row count are zero-filled so stale rows of the token-packed buffers contribute nothing.
-int transpose_pad_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, const int* dyn_rows,
-                       __nv_bfloat16* y, int Kp, cudaStream_t s);
-// two operands (same rows / Kp) in one launch; colsum0 (optional): colsum0[c] += sum_r x0[r][c] over the live
+// two operands (same rows / Kp) in one launch (x1 may be null); colsum0 (optional): colsum0[c] += sum_r x0[r][c] over the live
 // rows - the bias gradient of the dY operand, taken while the tile is in flight anyway
 int transpose_pad2_bf16(const __nv_bfloat16* x0, long long ldx0, int width0, __nv_bfloat16* y0,
                         const __nv_bfloat16* x1, long long ldx1, int width1, __nv_bfloat16* y1, int rows,
@@ -68,7 +66,6 @@ int colsum_bf16(const __nv_bfloat16* x, long long ldx, int rows, int width, cons
                 float scale, float* out, cudaStream_t s);
 int colsum_f32(const float* x, long long ldx, int rows, int width, float* out, cudaStream_t s);
 int scale_f32(float* x, long long n, float a, cudaStream_t s);
-int add_f32(const float* a, const float* b, long long n, float* out, cudaStream_t s);
 // dx = y > 0 ? dy : 0
 int relu_bwd_f32(const float* y, const float* dy, long long n, float* dx, cudaStream_t s);
 // dst (bf16 [*, width], already zero) row seq_off[b] = src[b] (fp32 [B, width]): the gradient of
@@ -104,16 +101,9 @@ int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const
 // ---- BatchNorm with batch statistics (frozen backbone under model.train(), TV:models/resnet.py:143-163) --
 // sum[c] += sum_r y[r,c], sumsq[c] += sum_r y[r,c]^2 over an NHWC bf16 tensor viewed as [rows, C]; C % 2 == 0.
 int bn_stats_bf16(const __nv_bfloat16* y, long long rows, int C, float* sum, float* sumsq, cudaStream_t s);
-// mean = sum/n, var = sumsq/n - mean^2 (biased); scale = gamma*rsqrt(var+eps), shift = beta - mean*scale;
-// running_mean/var (optional, the caller's nn.BatchNorm2d buffers) <- (1-m)*running + m*(mean, var*n/(n-1)).
-int bn_finalize(const float* sum, const float* sumsq, long long n, int C, const float* gamma, const float* beta,
-                float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                cudaStream_t s);
-// y = act(y*scale[c] + shift[c] (+ identity)) in place on [rows, C] bf16; C % 8 == 0.
-int bn_apply_bf16(__nv_bfloat16* y, long long rows, int C, const float* scale, const float* shift,
-                  const __nv_bfloat16* identity, int relu, cudaStream_t s);
-// The same with scale / shift derived on the fly from the batch sums (no separate finalize launch):
-// mean = sum/n, var = sumsq/n - mean^2, scale = gamma*rsqrt(var+eps), shift = beta - mean*scale.
+// y = act(y*scale[c] + shift[c] (+ identity)) in place on [rows, C] bf16 (C % 8 == 0), scale / shift derived per
+// block from the batch sums: mean = sum/n, var = sumsq/n - mean^2 (biased), scale = gamma*rsqrt(var+eps),
+// shift = beta - mean*scale.
 int bn_apply_stats_bf16(__nv_bfloat16* y, long long rows, int C, const float* sum, const float* sumsq,
                         const float* gamma, const float* beta, float eps, const __nv_bfloat16* identity, int relu,
                         cudaStream_t s);
@@ -128,10 +118,5 @@ struct BnSite {
     int C;
 };
 int bn_update_running(const BnSite* table, int sites, int max_C, float momentum, cudaStream_t s);
-
-// w [rows, cols] fp32 -> out[c][col_off + r] = bf16(w[r][c] * scale), out row stride ld_out: the
-// transposed (input-major) copy of an nn.Linear weight used as the B operand of dX = dY W.
-int pack_linear_t(const float* w, int rows, int cols, float scale, __nv_bfloat16* out, long long ld_out,
-                  int col_off, cudaStream_t s);
 
 }  // namespace mrd

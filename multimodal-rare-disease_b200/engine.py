@@ -106,6 +106,20 @@ class Engine:
     # frozen ResNet50 backbone - 53 BN-folded filters - is not re-packed every step)
     GROUPS = ("cnn_encoder.backbone.", "cnn_encoder.projection.", "text_encoder.", "fusion.", "classifier.")
 
+    @classmethod
+    def group_named(cls, named: Iterable[Tuple[str, torch.Tensor]]) -> Dict[str, list]:
+        """Floating-point (name, tensor) pairs bucketed by hand-over group; integer buffers
+        (num_batches_tracked) and names outside every group are dropped."""
+        groups = {g: [] for g in cls.GROUPS}
+        for n, t in named:
+            if not t.is_floating_point():
+                continue
+            for g in cls.GROUPS:
+                if n.startswith(g):
+                    groups[g].append((n, t))
+                    break
+        return groups
+
     def mark_dirty(self, group: str) -> None:
         """The library changed tensors of `group` behind torch's back (running statistics of the batch-norm
         layers in train mode): the next eval-mode hand-over re-packs the group."""
@@ -115,14 +129,7 @@ class Engine:
         """Re-pack the library's weights for every group in which a tensor was replaced or written since the
         last call.  named: (canonical state_dict name, tensor) pairs.  Returns True when a re-pack happened.
         training=True leaves a merely `dirty` backbone alone (its folded eval-mode copy is not used there)."""
-        groups = {g: [] for g in self.GROUPS}
-        for n, t in named:
-            if not t.is_floating_point():
-                continue
-            for g in self.GROUPS:
-                if n.startswith(g):
-                    groups[g].append((n, t))
-                    break
+        groups = self.group_named(named)
         changed = []
         for g, items in groups.items():
             if not items:

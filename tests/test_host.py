@@ -251,3 +251,21 @@ def test_predict_batch_formatting_matches_reference_semantics():
     assert res[1]["top_prediction"]["class_id"] == int(np.argsort(probs[1].numpy())[::-1][0])
     with pytest.raises(ValueError, match="must match"):
         mrd_b200.predict_batch_tensors(m, torch.zeros(2, 3, 8, 8), torch.zeros(3, 4, dtype=torch.long), None)
+
+
+def test_weight_handover_groups(model):
+    """Parameters are handed to the library in five independent groups (a training step re-packs the trainable
+    ones only); every floating-point state_dict entry lands in exactly one group."""
+    from importlib import import_module
+
+    Engine = import_module("multimodal-rare-disease_b200.engine").Engine
+    named = list(model._mrd_named())
+    groups = Engine.group_named(named)
+    assert list(groups) == ["cnn_encoder.backbone.", "cnn_encoder.projection.", "text_encoder.", "fusion.", "classifier."]
+    n_float = sum(1 for _, t in named if t.is_floating_point())
+    assert sum(len(v) for v in groups.values()) == n_float
+    assert len(groups["cnn_encoder.projection."]) == 4 and len(groups["classifier."]) == 6
+    assert all(n.startswith("cnn_encoder.backbone.") for n, _ in groups["cnn_encoder.backbone."])
+    # the frozen backbone is exactly the group a default-configuration training step never re-packs
+    assert not any(t.requires_grad for _, t in groups["cnn_encoder.backbone."])
+    assert all(t.requires_grad for _, t in groups["cnn_encoder.projection."])
