@@ -281,7 +281,8 @@ def main():
         def e2e_step():
             with torch.no_grad():
                 out = dp.forward_shard_host(
-                    lambda im, i, m, o: model.forward_host(im, i, m, micro_batch=args.micro_batch, logits_out=o),
+                    lambda im, i, m, o: model.forward_host(im, i, m, micro_batch=args.micro_batch, logits_out=o,
+                                                           next_batch=(im, i, m)),
                     h_images, h_ids, h_mask, total, dev)
                 h_logits.copy_(out, non_blocking=True)
 
@@ -303,7 +304,8 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_logits.numel() * 4,
                "ms_per_step": ems / args.steps,
                "path": "pinned host tensors -> MultimodalClassifier.forward_host (H2D of micro-batch i+1 on a copy "
-                       f"stream under the kernels of micro-batch i, micro_batch={args.micro_batch}) -> logits "
+                       f"stream under the kernels of micro-batch i, micro_batch={args.micro_batch}; the first micro-batch of the next "
+                       f"step is copied under the last one of this step, as a loader that holds the next batch would) -> logits "
                        "all-gather -> pinned host"}
 
     # ---------------------------------------------------------------- roofline: profiled step (rank 0)

@@ -233,13 +233,18 @@ class MultimodalClassifier(B200Module):
 
     def forward_host(self, images: torch.Tensor, input_ids: torch.Tensor,
                      attention_mask: Optional[torch.Tensor], micro_batch: int = 512, *,
-                     logits_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                     logits_out: Optional[torch.Tensor] = None, next_batch=None) -> Dict[str, torch.Tensor]:
         """forward() for batches that still live in HOST memory (what the reference's callers hold
         before `.to(device)`, src/train.py:252-255 / src/predict.py:220-238).
 
         The batch is cut into micro-batches; a copy stream moves micro-batch i+1 host->device (pinned
         memory makes the copies asynchronous) while the kernels of micro-batch i run, so the PCIe
         transfer (602 KB per image) hides behind the compute.  Returns device tensors like forward().
+
+        next_batch = (images, input_ids, attention_mask) of the NEXT call (what a data loader already holds):
+        its first micro-batch is copied while this call's last micro-batch computes, so the next call starts on
+        data that is already on the device instead of exposing one H2D copy per call.  The tensors must be the
+        very objects passed to the next call and must not be modified in between; anything else is ignored.
         """
         eng = self._engine()
         dev = eng.device
@@ -260,23 +265,42 @@ class MultimodalClassifier(B200Module):
         free = [None, None]         # kernels that read the staging slot finished
         n_mb = -(-B // mb)
 
+        def stage(imgs, ids_, mask_, lo, hi):
+            """H2D of rows [lo, hi) on the copy stream (must be current) -> (device tensors, done event)."""
+            m = None if mask_ is None else mask_[lo:hi].to(dev, non_blocking=True)
+            t = (imgs[lo:hi].to(dev, non_blocking=True), ids_[lo:hi].to(dev, non_blocking=True), m)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            return t, ev
+
         def issue_copy(i):
             slot = i & 1
             lo, hi = i * mb, min(B, (i + 1) * mb)
             with torch.cuda.stream(copy):
                 if free[slot] is not None:
                     copy.wait_event(free[slot])
-                m = None if attention_mask is None else attention_mask[lo:hi].to(dev, non_blocking=True)
-                staged[slot] = (images[lo:hi].to(dev, non_blocking=True),
-                                input_ids[lo:hi].to(dev, non_blocking=True), m)
-                ready[slot] = torch.cuda.Event()
-                ready[slot].record(copy)
+                staged[slot], ready[slot] = stage(images, input_ids, attention_mask, lo, hi)
 
-        copy.wait_stream(main)
-        issue_copy(0)
+        def batch_key(imgs, ids_, mask_, n, step):
+            return (id(imgs), id(ids_), id(mask_), int(n), int(step), imgs.data_ptr(), ids_.data_ptr())
+
+        pre = self.__dict__.pop("_mrd_prefetched", None)
+        if pre is not None and pre["key"] == batch_key(images, input_ids, attention_mask, B, mb) and pre["dev"] == dev:
+            staged[0], ready[0] = pre["tensors"], pre["event"]      # micro-batch 0 is already on its way
+        else:
+            copy.wait_stream(main)
+            issue_copy(0)
         for i in range(n_mb):
             if i + 1 < n_mb:
                 issue_copy(i + 1)
+            elif next_batch is not None and next_batch[0].shape[0] > 0:
+                nb_im, nb_ids, nb_mask = next_batch
+                B2 = nb_im.shape[0]
+                mb2 = max(1, min(micro_batch, B2))
+                with torch.cuda.stream(copy):
+                    tensors, ev = stage(nb_im, nb_ids, nb_mask, 0, min(B2, mb2))
+                self.__dict__["_mrd_prefetched"] = {"key": batch_key(nb_im, nb_ids, nb_mask, B2, mb2), "dev": dev,
+                                                    "tensors": tensors, "event": ev, "refs": next_batch}
             slot = i & 1
             lo, hi = i * mb, min(B, (i + 1) * mb)
             main.wait_event(ready[slot])

@@ -252,6 +252,23 @@ def test_forward_host_streams_match_device_forward(cuda, state):
     torch.cuda.synchronize()
     assert torch.equal(out["logits"], ref["logits"]) and torch.equal(out["probs"], ref["probs"])
     assert torch.equal(out2["logits"], _fwd(model, images, ids, None)["logits"])
+    # cross-call prefetch: the first micro-batch of the announced next batch is staged under this call's tail
+    a = (images.pin_memory(), ids.pin_memory(), mask.pin_memory())
+    imb, idb, mb_ = synth.make_inputs(5, 32, 124, [32, 8, 30, 2, 11], H=64, W=64)
+    b = (imb.pin_memory(), idb.pin_memory(), mb_.pin_memory())
+    ref_b = _fwd(model, imb, idb, mb_)
+    with torch.no_grad():
+        o1 = model.forward_host(*a, micro_batch=3, next_batch=b)
+        assert "_mrd_prefetched" in model.__dict__
+        o2 = model.forward_host(*b, micro_batch=3, next_batch=a)      # consumes the prefetch
+        o3 = model.forward_host(*b, micro_batch=3)                    # announced batch a, got b: prefetch dropped
+        assert "_mrd_prefetched" not in model.__dict__
+        o4 = model.forward_host(*a, micro_batch=8, next_batch=a)      # single micro-batch per call
+        o5 = model.forward_host(*a, micro_batch=8)
+    torch.cuda.synchronize()
+    assert torch.equal(o1["logits"], ref["logits"]) and torch.equal(o2["logits"], ref_b["logits"])
+    assert torch.equal(o3["logits"], ref_b["logits"]) and torch.equal(o3["probs"], ref_b["probs"])
+    assert torch.equal(o4["logits"], ref["logits"]) and torch.equal(o5["logits"], ref["logits"])
 
 
 def test_cls_tail_matches_full_last_layer(cuda, state):
