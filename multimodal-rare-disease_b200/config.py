@@ -13,44 +13,49 @@ from dataclasses import dataclass, field
 from typing import List
 
 
+SYNDROME_NAMES = ("Cornelia de Lange Syndrome", "Williams-Beuren Syndrome", "Noonan Syndrome", "Kabuki Syndrome",
+                  "KBG Syndrome", "Angelman Syndrome", "Rubinstein-Taybi Syndrome", "Smith-Magenis Syndrome",
+                  "Nicolaides-Baraitser Syndrome", "22q11.2 Deletion Syndrome")
+
+
 @dataclass
 class CNNEncoderConfig:
-    backbone: str = "resnet50"
-    pretrained: bool = True
+    backbone: str = "resnet50"            # the B200 path implements ResNet50 only (efficientnet_b0 raises)
+    pretrained: bool = True               # ImageNet weights through torchvision, as the reference does
     embedding_dim: int = 512
-    freeze_backbone: bool = True
-    freeze_layers: int = 6
+    freeze_backbone: bool = True          # the training step requires the backbone frozen (reference default)
+    freeze_layers: int = 6                # only read when freeze_backbone is False
     dropout: float = 0.5
 
 
 @dataclass
 class TextEncoderConfig:
-    model_name: str = "dmis-lab/biobert-base-cased-v1.2"
+    model_name: str = "dmis-lab/biobert-base-cased-v1.2"   # any BERT-base shaped checkpoint
     embedding_dim: int = 768
-    max_length: int = 128
-    freeze_embeddings: bool = False
+    max_length: int = 128                 # tokenizer side; the kernels take S <= 512
+    freeze_embeddings: bool = False       # frozen parameters simply get no gradient slot
     freeze_layers: int = 0
     dropout: float = 0.1
-    use_pooler_output: bool = False
+    use_pooler_output: bool = False       # True is outside the path (CLS row of the last layer is used)
 
 
 @dataclass
 class FusionConfig:
-    fusion_type: str = "attention"
+    fusion_type: str = "attention"        # concatenation / gated are outside the path
     hidden_dim: int = 512
-    num_attention_heads: int = 8
+    num_attention_heads: int = 8          # heads of the two length-1 cross attentions
     dropout: float = 0.3
-    use_residual: bool = True
-    image_proj_dim: int = 512
-    text_proj_dim: int = 768
+    use_residual: bool = True             # LayerNorm(proj + attended) vs LayerNorm(attended)
+    image_proj_dim: int = 512             # = CNNEncoderConfig.embedding_dim
+    text_proj_dim: int = 768              # = BERT hidden size
 
 
 @dataclass
 class ClassifierConfig:
     hidden_dims: List[int] = field(default_factory=lambda: [256, 128])
-    num_classes: int = 10
+    num_classes: int = 10                 # the final GEMV + softmax kernel handles up to 32
     dropout: float = 0.5
-    activation: str = "relu"
+    activation: str = "relu"              # relu / gelu in eval mode, relu in the training step
 
 
 @dataclass
@@ -59,21 +64,9 @@ class Config:
     text_encoder: TextEncoderConfig = field(default_factory=TextEncoderConfig)
     fusion: FusionConfig = field(default_factory=FusionConfig)
     classifier: ClassifierConfig = field(default_factory=ClassifierConfig)
-    syndrome_names: List[str] = field(
-        default_factory=lambda: [
-            "Cornelia de Lange Syndrome",
-            "Williams-Beuren Syndrome",
-            "Noonan Syndrome",
-            "Kabuki Syndrome",
-            "KBG Syndrome",
-            "Angelman Syndrome",
-            "Rubinstein-Taybi Syndrome",
-            "Smith-Magenis Syndrome",
-            "Nicolaides-Baraitser Syndrome",
-            "22q11.2 Deletion Syndrome",
-        ]
-    )
-    seed: int = 42
+    # class index -> syndrome label, the order the reference's classification head is trained with
+    syndrome_names: List[str] = field(default_factory=lambda: list(SYNDROME_NAMES))
+    seed: int = 42                        # kept for the callers; nothing here draws random numbers
 
 
 config = Config()
