@@ -63,6 +63,9 @@ class B200Module(nn.Module):
             self.training = training
 
     def __getstate__(self):
+        # runtime-only state never travels with pickles / deep copies: the engine (a device context), the copy
+        # stream and prefetched device tensors of forward_host, and the process group of data_parallel()
         d = self.__dict__.copy()
-        d.pop("_mrd_engine", None)
+        for k in ("_mrd_engine", "_mrd_copy_stream", "_mrd_prefetched", "_mrd_ddp"):
+            d.pop(k, None)
         return d

@@ -48,6 +48,7 @@ class Engine:
         self.lib = _lib.load()
         self.device = device
         self.train_serial = 0
+        self.train_opts: Optional[Dict[str, float]] = None   # "train.*" options applied to THIS context
         self._sigs: Dict[str, tuple] = {}
         self._dirty = set()
         self._keep: Dict[str, list] = {}

@@ -192,17 +192,24 @@ class MultimodalClassifier(B200Module):
             raise NotImplementedError("the fusion dropouts must share one probability (FusionConfig.dropout)")
         eng = self._engine(allow_training=True)
         opts = self._train_options()
-        if self.__dict__.get("_mrd_train_opts") != opts:
+        if eng.train_opts != opts:
+            # the cache of what was applied lives on the Engine: a new engine (model.to(other device), deepcopy,
+            # unpickling) starts from the library defaults and gets every option again
             for k, v in opts.items():
                 eng.set_option(k, v)
             # the optimizer rewrites the parameters every step: re-pack them in stream order instead of
             # stalling the host on a device synchronisation per step (the engine keeps the tensors alive)
             eng.set_option("load_sync", 0.0)
-            self.__dict__["_mrd_train_opts"] = opts
+            eng.train_opts = dict(opts)
         named = self._trainable()
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
         shapes = tuple((n, tuple(p.shape)) for n, p in named)
         ddp = self.__dict__.get("_mrd_ddp", (False, None))
+        if ddp[0]:
+            # every rank usually runs under the same torch.manual_seed: without this all ranks would apply the
+            # same dropout masks to their shards (masks are a pure function of seed, site and element index)
+            from .parallel import rank_seed
+            seed = rank_seed(seed, ddp[1])
         logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes,
                                   (self.num_classes, ddp[0], ddp[1]), *[p for _, p in named])
         if opts["train.bn_train"]:
@@ -214,6 +221,14 @@ class MultimodalClassifier(B200Module):
             if counters:
                 torch._foreach_add_(counters, 1)
             eng.mark_dirty("cnn_encoder.backbone.")
+            if ddp[0]:
+                # DistributedDataParallel(broadcast_buffers=True) semantics: rank 0's running statistics are the
+                # model's (each rank computed them from its own shard), so the ranks' eval-mode models and any
+                # rank's checkpoint stay identical
+                from .parallel import broadcast_buffers_
+                broadcast_buffers_([b for m in self.cnn_encoder.backbone.modules()
+                                    if isinstance(m, nn.modules.batchnorm._BatchNorm)
+                                    for b in (m.running_mean, m.running_var) if b is not None], ddp[1])
         return {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
 
     def data_parallel(self, enabled: bool = True, process_group=None) -> "MultimodalClassifier":

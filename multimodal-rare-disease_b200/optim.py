@@ -123,5 +123,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 pl["chunk_t"].numel(), _CHUNK, float(b1), float(b2), float(self.param_groups[0]["eps"]),
                 steps.pop(), self.max_grad_norm, pl["sq"].data_ptr(),
                 C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "mrd_adamw_step")
+        # the kernel wrote the parameters through raw pointers: bump their torch version counters so that everything
+        # keyed on `_version` sees the update (Engine.sync_weights re-packs the library's bf16 copies of a group only
+        # when a (data_ptr, _version) signature changed; autograd's saved-tensor checks rely on it as well)
+        torch.autograd.graph.increment_version([p for p, _ in items if p.grad is not None])
         self.last_grad_norm = pl["sq"].sqrt()
         return loss

@@ -109,3 +109,45 @@ def allreduce_mean_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = Non
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.mul_(1.0 / world)
     return flat
+
+
+def allreduce_mean_async(bucket: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """Starts the averaging all-reduce of one gradient bucket and returns a handle for wait_allreduce (None
+    without a process group).  The training backward hands over its flat gradient buffer bucket by bucket while
+    the remaining layers are still being differentiated (bucketed, overlapped)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return (work, bucket, dist.get_world_size(group))
+
+
+def wait_allreduce(handle) -> None:
+    if handle is None:
+        return
+    work, bucket, world = handle
+    work.wait()
+    bucket.mul_(1.0 / world)
+
+
+def rank_seed(seed: int, group: Optional[dist.ProcessGroup] = None) -> int:
+    """Per-rank dropout seed for data-parallel training: the step seed mixed with the rank (rank 0 keeps the
+    single-process seed), so shards do not share dropout masks when every rank seeds torch identically."""
+    if not dist.is_initialized():
+        return seed
+    rank = dist.get_rank(group)
+    return (seed ^ (rank * 0x9E3779B97F4A7C15)) & 0x3FFFFFFFFFFFFFFF
+
+
+def broadcast_buffers_(buffers, group: Optional[dist.ProcessGroup] = None, src: int = 0) -> None:
+    """Overwrite `buffers` (BatchNorm running statistics) on every rank with rank `src`'s values: one flat
+    broadcast, as DistributedDataParallel does with broadcast_buffers=True."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or not buffers:
+        return
+    flat = torch.cat([b.detach().reshape(-1).float() for b in buffers])
+    dist.broadcast(flat, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    off = 0
+    with torch.no_grad():
+        for b in buffers:
+            n = b.numel()
+            b.copy_(flat[off:off + n].view_as(b))
+            off += n

@@ -49,7 +49,9 @@ def predict_batch_tensors(model, images: torch.Tensor, input_ids: torch.Tensor,
     Host tensors should be pinned for the copies to overlap the kernels."""
     if images.shape[0] != input_ids.shape[0]:
         raise ValueError("Number of images must match number of texts")   # src/predict.py:214
-    was_training = model.training
+    # model.train(flag) recurses: a model trained as `model.train(); model.cnn_encoder.backbone.eval()` must come
+    # back with exactly the per-module flags it had (or the next step would switch BatchNorm to batch statistics)
+    modes = [(m, m.training) for m in model.modules()]
     model.eval()
     try:
         if images.device.type == "cpu":
@@ -58,4 +60,5 @@ def predict_batch_tensors(model, images: torch.Tensor, input_ids: torch.Tensor,
             out = model(images=images, input_ids=input_ids, attention_mask=attention_mask)
         return format_predictions(out["probs"], class_names, top_k)
     finally:
-        model.train(was_training)
+        for m, flag in modes:
+            m.training = flag

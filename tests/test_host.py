@@ -111,6 +111,43 @@ def test_deepcopy_and_pickle_drop_engine(model):
     pickle.loads(pickle.dumps(model.classifier))
 
 
+def test_getstate_drops_runtime_state(model):
+    """Pickles / deep copies carry parameters only: no engine, copy stream, prefetched device tensors or process
+    group, and no cache of applied train options (that lives on the Engine, so a new engine gets them again)."""
+    import copy
+
+    model.__dict__["_mrd_copy_stream"] = object()
+    model.__dict__["_mrd_prefetched"] = {"x": 1}
+    model.__dict__["_mrd_ddp"] = (True, None)
+    try:
+        m2 = copy.deepcopy(model)
+        for k in ("_mrd_engine", "_mrd_copy_stream", "_mrd_prefetched", "_mrd_ddp", "_mrd_train_opts"):
+            assert k not in m2.__dict__, k
+    finally:
+        for k in ("_mrd_copy_stream", "_mrd_prefetched", "_mrd_ddp"):
+            model.__dict__.pop(k, None)
+
+
+def test_predict_batch_restores_per_module_modes(model, monkeypatch):
+    """predict_batch_tensors puts back every module's own training flag (backbone.eval() inside model.train())."""
+    from importlib import import_module
+    pred = import_module("multimodal-rare-disease_b200.predict")
+    model.train()
+    model.cnn_encoder.backbone.eval()
+    try:
+        monkeypatch.setattr(type(model), "forward",
+                            lambda self, images=None, input_ids=None, attention_mask=None, **k:
+                            {"probs": torch.full((images.shape[0], 10), 0.1)})
+        # a non-CPU, non-CUDA device tag routes through model(...) (the patched forward) instead of forward_host
+        images = torch.zeros(2, 3, 8, 8, device="meta")
+        pred.predict_batch_tensors(model, images, torch.zeros(2, 4, dtype=torch.long), None)
+        assert model.training and model.text_encoder.training
+        assert not model.cnn_encoder.backbone.training
+        assert not any(m.training for m in model.cnn_encoder.backbone.modules())
+    finally:
+        model.eval()
+
+
 def test_shard_bounds():
     for total in (0, 1, 7, 16, 4096, 4099):
         for world in (1, 2, 3, 8):
@@ -167,11 +204,27 @@ def _ar_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        from importlib import import_module
+        par = import_module("multimodal-rare-disease_b200.parallel")
         flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
         views = [flat[:4].view(2, 2), flat[4:]]          # parameter gradients are views of the bucket
         mrd_b200.allreduce_mean_(flat)
         want = torch.arange(10, dtype=torch.float32) * 1.5
-        q.put((rank, torch.equal(flat, want), torch.equal(views[0], want[:4].view(2, 2))))
+        ok = torch.equal(flat, want) and torch.equal(views[0], want[:4].view(2, 2))
+        # bucketed variant (the overlapped path): same result bucket by bucket
+        flat2 = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        works = [par.allreduce_mean_async(flat2[a:b]) for a, b in ((6, 10), (2, 6), (0, 2))]
+        for w in works:
+            par.wait_allreduce(w)
+        ok = ok and torch.equal(flat2, want)
+        # per-rank dropout seeds differ, rank 0 keeps the caller's seed
+        s = par.rank_seed(12345)
+        ok = ok and ((s == 12345) if rank == 0 else (s != 12345)) and 0 <= s < 2 ** 62
+        # BatchNorm buffers: rank 0's values everywhere
+        bufs = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
+        par.broadcast_buffers_(bufs)
+        ok = ok and torch.equal(bufs[0], torch.ones(3)) and torch.equal(bufs[1], torch.full((2, 2), 10.0))
+        q.put((rank, ok, True))
     finally:
         dist.destroy_process_group()
 
@@ -235,6 +288,9 @@ def test_predict_batch_formatting_matches_reference_semantics():
 
         def train(self, mode=True):
             self.training = mode
+
+        def modules(self):
+            return [self]
 
         def forward_host(self, images, ids, mask, micro_batch=512):
             self.calls.append(("host", micro_batch, self.training))

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import mrd_b200
 import synth
 from oracle import train_oracle as T
 
@@ -636,3 +637,54 @@ def test_train_mode_refuses_what_it_cannot_do(cuda):
     model.cnn_encoder.backbone.layer4.requires_grad_(True)
     with pytest.raises(NotImplementedError, match="backbone"):
         model(images.cuda(), ids.cuda(), mask.cuda())
+
+
+def test_fused_adamw_drives_the_model(cuda, sens):
+    """FusedAdamW writes the parameters through raw pointers; the library's packed bf16 copies (BERT GEMM weights,
+    their transposed dgrad copies, the eval-mode packs) must follow.  Four steps with FusedAdamW(max_grad_norm=1)
+    against four steps of clip_grad_norm_ + torch.optim.AdamW on an identical model: the train-mode logits of every
+    step and the eval-mode logits afterwards agree to a small fraction of how far the training moved them."""
+    images, ids, mask = synth.make_inputs(8, 32, 77, [32, 20, 7, 1, 32, 15, 9, 28], H=64, W=64)
+    images, ids, mask = images.cuda(), ids.cuda(), mask.cuda()
+    labels = torch.tensor([3, 1, 7, 3, 0, 9, 2, 5]).cuda()
+    lr = 1e-3   # large enough that four steps move the logits far above the bf16 noise
+    runs = {}
+    for kind in ("torch", "fused"):
+        model = _train_model(sens)
+        params = list(model.parameters())
+        versions = [p._version for p in params]
+        opt = (mrd_b200.FusedAdamW(params, lr=lr, weight_decay=0.05, max_grad_norm=1.0) if kind == "fused"
+               else torch.optim.AdamW(params, lr=lr, weight_decay=0.05))
+        model.eval()
+        with torch.no_grad():
+            e0 = model(images, ids, mask)["logits"].clone()
+        model.train()
+        model.cnn_encoder.backbone.eval()
+        steps = []
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            out = model(images, ids, mask)["logits"]
+            steps.append(out.detach().clone())
+            nn.CrossEntropyLoss()(out, labels).backward()
+            if kind == "torch":
+                nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        if kind == "fused":
+            bumped = [p._version > v for p, v in zip(params, versions) if p.grad is not None]
+            assert bumped and all(bumped), "FusedAdamW must bump the version counter of every parameter it updates"
+        model.eval()
+        with torch.no_grad():
+            e1 = model(images, ids, mask)["logits"].clone()
+        torch.cuda.synchronize()
+        runs[kind] = (e0, steps, e1)
+    (e0a, sa, e1a), (e0b, sb, e1b) = runs["torch"], runs["fused"]
+    assert torch.equal(e0a, e0b)
+    moved_train = (sa[-1] - sa[0]).norm().item()
+    moved_eval = (e1a - e0a).norm().item()
+    assert moved_train > 0.05 and moved_eval > 0.05, (moved_train, moved_eval)   # the case does train
+    for i, (a, b) in enumerate(zip(sa, sb)):
+        assert (a - b).norm().item() <= 0.05 * moved_train, (i, (a - b).norm().item(), moved_train)
+    d_eval = (e1a - e1b).norm().item()
+    print(f"fused vs torch AdamW after 4 steps: train logits moved {moved_train:.3f}, eval logits moved "
+          f"{moved_eval:.3f}, eval difference {d_eval:.4f}")
+    assert d_eval <= 0.05 * moved_eval, (d_eval, moved_eval)
