@@ -173,7 +173,7 @@ def _config(args, world):
             "global_batch": args.global_batch, "per_gpu_batch": -(-args.global_batch // world),
             "seq_len": SEQ, "image": IMG, "parallelism": f"dp{world}",
             "l2": "per-rank inputs exceed L2 (>= 308 MB vs 126 MB); no flush between steps",
-            "img_chunk": args.img_chunk, "tok_chunk": args.tok_chunk}
+            "img_chunk": args.img_chunk, "tok_chunk": args.tok_chunk, "engine_opts": args.engine_opt}
 
 
 def _timed_ms(fn, iters, warmup):
@@ -278,6 +278,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--engine-opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="mrd_ctx_set_option switches for A/B runs, e.g. fuse_ds=0")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short timings of configs[1], [2] and [4] in the N=1 line")
     args = ap.parse_args()
@@ -321,6 +323,9 @@ def main():
     model = synth.build_model(0).to(dev)
     model.configure_b200(args.img_chunk, args.tok_chunk)
     eng = model._engine()
+    for kv in args.engine_opt:
+        k, v = kv.split("=", 1)
+        eng.set_option(k, float(v))
     dp = mrd_b200.DataParallelForward(
         lambda im, i, m, out: model(im, i, m, logits_out=out), model.num_classes)
 

@@ -53,7 +53,10 @@ int mrd_ctx_destroy(mrd_ctx* ctx);
 int mrd_ctx_configure(mrd_ctx* ctx, int img_chunk, int seq_chunk_tokens);
 
 /* Scalar options: "bert_heads" (12), "bert_ln_eps" (1e-12), "bn_eps" (1e-5), "fusion_ln_eps" (1e-5),
- * "fusion_heads" (8), "fusion_residual" (1), "head_act" (MRD_ACT_RELU).  Set before load_weights. */
+ * "fusion_heads" (8), "fusion_residual" (1), "head_act" (MRD_ACT_RELU).  Set before load_weights.
+ * "fuse_ds" (1): run conv3 + downsample of each stage's first bottleneck as one K-concatenated GEMM
+ * (mrd_conv1x1_dual_bf16); 0 = separate downsample launch + residual read (A/B switch, same results up to
+ * the bf16 rounding of the downsample output that the fused form never materialises). */
 int mrd_ctx_set_option(mrd_ctx* ctx, const char* key, double value);
 
 /* Hands the context the model's fp32 parameters/buffers by their state_dict names
@@ -142,6 +145,14 @@ int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void
                          int ksize, int stride, const float* bias, void* Y, const void* residual,
                          int act, int out_pad, void* stream);
 
+/* conv3 + downsample + residual add + ReLU of a bottleneck's FIRST block (TV:143-163 with self.downsample) as one
+ * GEMM over the concatenated K: Y = act(X0 * Wcat[:, :C0]^T + X1[:, ::stride, ::stride] * Wcat[:, C0:]^T + bias).
+ * X0: [N,Ho,Wo,C0] bf16 (conv2 output), X1: [N,Ho*stride,Wo*stride,C1] bf16 (block input), stride in {1,2};
+ * Wcat: [Cout][C0+C1] bf16 (both BN scales folded), bias: f32 [Cout] = sum of the two folded BN shifts.
+ * The downsample branch's output is never written to memory.  C0, C1, Cout % 64 == 0. */
+int mrd_conv1x1_dual_bf16(const void* X0, int C0, const void* X1, int C1, int stride, int N, int Ho, int Wo,
+                          const void* Wcat, int Cout, const float* bias, void* Y, int act, void* stream);
+
 /* Conv2d(3, stride 1, pad 1) + folded BN + activation in flat-shift mode: Xpad is the zero-bordered
  * [N][H+2][W+2][Cin] bf16 input; the halo span of each tile is fetched once per 64-channel chunk and
  * the 9 taps are row-shifted tcgen05 views of it (TV:143-163 conv2 of layer1/layer2).  W <= 62. */
@@ -229,6 +240,19 @@ int mrd_train_forward(mrd_ctx* ctx, const void* images, int img_dtype, const lon
  * (softmax over one key, src/fusion_model.py:138-165), the BERT pooler is unused. */
 int mrd_train_backward(mrd_ctx* ctx, const float* dlogits, int n, const char* const* names,
                        float* const* grads, void* stream);
+
+/* The same two calls with the extra tensors Grad-CAM needs (notebooks/explainability.ipynb cell 3 hooks
+ * cnn_encoder.get_attention_layer() = backbone.layer4, src/cnn_encoder.py:186-198, and back-propagates one logit):
+ * feat_map (optional): f32 [B,2048,H/32,W/32] NCHW, the layer4 output of this forward (BatchNorm on running
+ * statistics only); d_pooled (optional): f32 [B,2048] = d(loss)/d(backbone output after global average pooling), from
+ * which d(loss)/d(layer4 output) = d_pooled / (H/32 * W/32) at every position.  With every dropout probability 0
+ * this is the eval-mode forward made differentiable.  When no text_encoder.* gradient is requested the text branch
+ * of the backward is skipped. */
+int mrd_train_forward_ex(mrd_ctx* ctx, const void* images, int img_dtype, const long long* ids,
+                         const void* mask, int mask_dtype, int B, int H, int W, int S,
+                         unsigned long long seed, float* logits, float* feat_map, void* stream);
+int mrd_train_backward_ex(mrd_ctx* ctx, const float* dlogits, int n, const char* const* names,
+                          float* const* grads, float* d_pooled, void* stream);
 
 /* out[i] = 1 if element i of dropout site `site` is kept under (seed, p), else 0 (i < n).  The masks
  * of mrd_train_forward are reproducible with this (tests; csrc/rng.cuh documents the site ids and the

@@ -47,6 +47,16 @@ int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }
 
+int mrd_conv1x1_dual_bf16(const void* X0, int C0, const void* X1, int C1, int stride, int N, int Ho, int Wo,
+                          const void* Wcat, int Cout, const float* bias, void* Y, int act, void* stream) {
+    GemmLaunch g;
+    int rc = plan_conv1x1_dual(&g, static_cast<const __nv_bfloat16*>(X0), C0, static_cast<const __nv_bfloat16*>(X1),
+                               C1, stride, N, Ho, Wo, static_cast<const __nv_bfloat16*>(Wcat), Cout, bias,
+                               static_cast<__nv_bfloat16*>(Y), act);
+    if (rc) return rc;
+    return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
 int mrd_conv3x3_flat_bf16(const void* Xpad, int N, int H, int W, int Cin, const void* Wt, int Cout,
                           const float* bias, void* Y, int act, void* stream) {
     GemmLaunch g;

@@ -81,6 +81,20 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* bas
     }
 }
 
+// bar.sync with an OR reduction of one predicate over the participating threads
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.cta.red.or.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(static_cast<uint32_t>(pred)), "r"(id), "r"(nthreads)
+        : "memory");
+    return r != 0;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -481,8 +495,12 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
         } else {
             // ------------------------------------------------ softmax warps: thread = query row
             const int row = tid;  // 0..127 == TMEM lane
-            bias_s[row] = row < len ? (p.bias ? __ldg(p.bias + off + row) : 0.0f) : -INFINITY;
-            named_bar_sync(1, 128);
+            const float my_bias = row < len ? (p.bias ? __ldg(p.bias + off + row) : 0.0f) : -INFINITY;
+            bias_s[row] = my_bias;
+            // token-packed batches carry no key bias at all except on a masked [CLS] row: when every key of the
+            // item is plain (bias 0) the inner loops skip the per-key bias (one shared-memory load, one add and one
+            // select per score) and only bound the columns by the length
+            const bool biased = named_bar_or(1, 128, row < len && my_bias != 0.0f);
             const uint32_t t_row = tm + (static_cast<uint32_t>(warp * 32) << 16);
             mbar_wait(s_bar, phase);
             tc_fence_after();
@@ -492,8 +510,13 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
                 uint32_t v[32];
                 tmem_ld32(t_row + c0, v);
                 tmem_ld_wait();
+                if (!biased && c0 + 32 <= len) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) + bias_s[c0 + j]);
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) + bias_s[c0 + j]);
+                }
             }
             const float ms = (mx == -INFINITY ? 0.0f : mx) * kLog2e;
             // pass 2: probabilities -> bf16 A operand (K-major, two 64-key swizzle atoms over Q|K)
@@ -503,11 +526,22 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
                 tmem_ld32(t_row + c0, v);
                 tmem_ld_wait();
                 float e[32];
+                if (!biased && c0 + 32 <= len) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    e[j] = fast_exp2(fmaf(__uint_as_float(v[j]) + bias_s[c0 + j], kLog2e, -ms));
-                    sum += e[j];
-                    if (DROP) {
+                    for (int j = 0; j < 32; ++j) {
+                        e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), kLog2e, -ms));
+                        sum += e[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        e[j] = fast_exp2(fmaf(__uint_as_float(v[j]) + bias_s[c0 + j], kLog2e, -ms));
+                        sum += e[j];
+                    }
+                }
+                if (DROP) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
                         const unsigned long long idx =
                             (static_cast<unsigned long long>(item) * p.S_max + row) * p.S_max + (c0 + j);
                         e[j] = drop_keep(p.drop, idx) ? e[j] * p.drop.scale : 0.0f;
@@ -569,6 +603,380 @@ attention_tc_kernel(const __grid_constant__ TcParams p) {
     }
 }
 
+// ====================================================================== tcgen05 path (128 < S <= 512)
+// One work item = one (sample, head, block of 128 queries).  The keys are walked in blocks of 128; per block
+//   control warp (lane 0): S_j = Q K_j^T into TMEM; K_{j+1} | V_{j+1} (also across items) are already on their
+//       way into the other shared-memory buffer, and the next item's Q is fetched as soon as the last S of this
+//       item has been consumed, so no TMA latency sits on the per-block chain;
+//   softmax warps (thread = query row = TMEM lane): block maximum, running maximum m, P_j = exp(S_j - m) as the
+//       bf16 K-major A operand over the consumed K_j tile (+16 KB), running sum l;
+//   control warp: O_j = P_j V_j into the TMEM columns S_j occupied;
+//   softmax warps: acc = acc * exp(m_old - m) + O_j with the 64 accumulators of the row in REGISTERS (the flash
+//       recurrence; HF:integrations/sdpa_attention.py:92 computes the same softmax(QK^T + mask) V in one piece),
+// and the row is normalised by 1/l and stored after the last block.  Nothing but Q, K, V is read and nothing but
+// the output written: scores and probabilities never leave the SM.  Every barrier completes one phase per key
+// block (counted in `it` by every role alike); two CTAs share an SM (99 KB smem, 128 TMEM columns each) so one
+// CTA's softmax overlaps the other's MMAs.
+struct TcLongParams {
+    CUtensorMap qkv_map[4];  // boxes of 32 / 64 / 96 / 128 rows
+    const float* bias;       // per row (packed) or [B,S] (dense); may be null
+    const int* seq_off;      // packed layout or null
+    __nv_bfloat16* out;
+    int S_max, heads, qblocks, items;
+    DropCfg drop;
+};
+
+constexpr int kTcLongData = 6 * 16384;   // Q | K0 | V0 | K1 | V1 | second P atom
+constexpr int kTcLongSmem = kTcLongData + 2048 + 256 + 1024;
+
+struct TcLongBlock {   // one (item, key block) of a CTA's work list
+    int item, j, nkv, off, len, q0, qlen, h, bh;
+    bool valid;
+};
+
+__device__ __forceinline__ bool tc_long_item(const TcLongParams& p, int item, TcLongBlock* o) {
+    o->item = item;
+    o->bh = item / p.qblocks;
+    const int qb = item - o->bh * p.qblocks;
+    const int b = o->bh / p.heads;
+    o->h = o->bh - b * p.heads;
+    int off, len;
+    if (p.seq_off) {
+        off = __ldg(p.seq_off + b);
+        len = __ldg(p.seq_off + b + 1) - off;
+    } else {
+        off = b * p.S_max;
+        len = p.S_max;
+    }
+    len = len > kMaxS ? kMaxS : len;
+    o->off = off;
+    o->len = len;
+    o->q0 = qb * 128;
+    o->j = 0;
+    if (o->q0 >= len) return false;   // query block beyond the sequence: nothing to do
+    o->qlen = len - o->q0 < 128 ? len - o->q0 : 128;
+    o->nkv = (len + 127) >> 7;
+    return true;
+}
+// first block of the first non-empty item at or after `item` (items are strided by the grid size)
+__device__ __forceinline__ TcLongBlock tc_long_first(const TcLongParams& p, int item, int stride) {
+    TcLongBlock b;
+    b.valid = false;
+    for (; item < p.items; item += stride)
+        if (tc_long_item(p, item, &b)) {
+            b.valid = true;
+            return b;
+        }
+    return b;
+}
+__device__ __forceinline__ TcLongBlock tc_long_next(const TcLongParams& p, const TcLongBlock& c, int stride) {
+    if (c.j + 1 < c.nkv) {
+        TcLongBlock n = c;
+        ++n.j;
+        return n;
+    }
+    return tc_long_first(p, c.item + stride, stride);
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_tc_long_kernel(const __grid_constant__ TcLongParams p) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t q_s = base;
+    const uint32_t x_s = base + 5 * 16384;                 // second 64-key atom of P
+    auto k_smem = [&](int buf) { return base + 16384u + static_cast<uint32_t>(buf) * 32768u; };
+    auto v_smem = [&](int buf) { return base + 32768u + static_cast<uint32_t>(buf) * 32768u; };
+    float* bias_s = reinterpret_cast<float*>(gen + kTcLongData);          // [512]
+    const uint32_t bars = base + kTcLongData + 2048;
+    const uint32_t s_bar = bars + 16, p_bar = bars + 24, o_bar = bars + 32, t_bar = bars + 40, q_bar = bars + 48;
+    auto full_bar = [&](int buf) { return bars + 8u * buf; };
+    volatile uint32_t* tslot = reinterpret_cast<volatile uint32_t*>(gen + kTcLongData + 2048 + 64);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // rows a short block does not fetch keep the previous contents (finite, masked or multiplied by zero)
+    for (int i = tid; i < kTcLongData / 16; i += kTcThreads) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.qkv_map[i]);
+        mbar_init(full_bar(0), 1);
+        mbar_init(full_bar(1), 1);
+        mbar_init(s_bar, 1);
+        mbar_init(p_bar, 128);
+        mbar_init(o_bar, 1);
+        mbar_init(t_bar, 128);
+        mbar_init(q_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<128>(bars + 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tslot;
+    const long long ldo = static_cast<long long>(p.heads) * kHeadDim;
+    const int stride = static_cast<int>(gridDim.x);
+
+    if (warp == 4) {
+        // ------------------------------------------------ control: TMA + MMA issue (one thread)
+        if (lane == 0) {
+            auto load_kv = [&](const TcLongBlock& blk, int buf) {
+                const int klen = blk.len - blk.j * 128 < 128 ? blk.len - blk.j * 128 : 128;
+                const int bk = (klen - 1) >> 5;
+                mbar_expect_tx(full_bar(buf), 2u * 4096u * static_cast<uint32_t>(bk + 1));
+                tma_load_3d(&p.qkv_map[bk], full_bar(buf), k_smem(buf), 0, blk.off + blk.j * 128, p.heads + blk.h);
+                tma_load_3d(&p.qkv_map[bk], full_bar(buf), v_smem(buf), 0, blk.off + blk.j * 128, 2 * p.heads + blk.h);
+            };
+            auto load_q = [&](const TcLongBlock& blk) {
+                const int bq = (blk.qlen - 1) >> 5;
+                mbar_expect_tx(q_bar, 4096u * static_cast<uint32_t>(bq + 1));
+                tma_load_3d(&p.qkv_map[bq], q_bar, q_s, 0, blk.off + blk.q0, blk.h);
+            };
+            TcLongBlock cur = tc_long_first(p, static_cast<int>(blockIdx.x), stride);
+            uint32_t q_phase = 0;
+            if (cur.valid) {
+                load_q(cur);
+                load_kv(cur, 0);
+            }
+            for (int it = 0; cur.valid; ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = it & 1u, prev = ph ^ 1u;
+                const TcLongBlock nxt = tc_long_next(p, cur, stride);
+                const int klen = cur.len - cur.j * 128 < 128 ? cur.len - cur.j * 128 : 128;
+                const int n16 = (klen + 15) & ~15;
+                // the other buffer (K, V and the P atom over K) was last read by the P V product of block it-1
+                if (it > 0) mbar_wait(o_bar, prev);
+                if (nxt.valid) load_kv(nxt, buf ^ 1);
+                mbar_wait(full_bar(buf), static_cast<uint32_t>(it >> 1) & 1u);
+                if (cur.j == 0) {
+                    mbar_wait(q_bar, q_phase);
+                    q_phase ^= 1u;
+                }
+                if (it > 0) mbar_wait(t_bar, prev);   // O of the previous block read out of TMEM
+                tc_fence_after();
+                {   // S[128 x n16] = Q K_j^T
+                    const uint32_t idesc = make_idesc_bf16(128, n16, 0, 0);
+                    const uint64_t adesc = make_smem_desc(q_s, 0, 1024, 2);
+                    const uint64_t bdesc = make_smem_desc(k_smem(buf), 0, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(tm, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+                    umma_commit(s_bar);
+                }
+                mbar_wait(p_bar, ph);   // every softmax thread has read S and written P: S (and Q, if last) is consumed
+                tc_fence_after();
+                if (nxt.valid && nxt.j == 0) load_q(nxt);   // Q of the next item streams in under P V and the O read-out
+                {   // O_j[128 x 64] = P_j[128 x n16] V_j[n16 x 64]; V rows are keys: MN-major B
+                    const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+                    for (int k = 0; k < n16 / 16; ++k) {
+                        const uint32_t pa = (k < 4 ? k_smem(buf) : x_s) + (k & 3) * 32;
+                        const uint64_t adesc = make_smem_desc(pa, 0, 1024, 2);
+                        const uint64_t bdesc = make_smem_desc(v_smem(buf) + k * 2048, 0, 1024, 2);
+                        umma_bf16(tm, adesc, bdesc, idesc, k != 0);
+                    }
+                    umma_commit(o_bar);
+                }
+                cur = nxt;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------ softmax warps: thread = query row
+        const int row = tid;  // 0..127 == TMEM lane
+        const uint32_t t_row = tm + (static_cast<uint32_t>(warp * 32) << 16);
+        int it = 0;
+        for (TcLongBlock cur = tc_long_first(p, static_cast<int>(blockIdx.x), stride); cur.valid;
+             cur = tc_long_first(p, cur.item + stride, stride)) {
+            // all 128 threads are past the previous item's last P write (its o_bar needed every p_bar arrival)
+#pragma unroll
+            for (int i = 0; i < kMaxS / 128; ++i) {
+                const int key = i * 128 + row;
+                bias_s[key] = key < cur.len ? (p.bias ? __ldg(p.bias + cur.off + key) : 0.0f) : -INFINITY;
+            }
+            bool nz = false;
+#pragma unroll
+            for (int i = 0; i < kMaxS / 128; ++i) nz |= (i * 128 + row < cur.len) && bias_s[i * 128 + row] != 0.0f;
+            // no key of the item carries a bias (the normal case of a token-packed batch): the inner loops then
+            // skip the per-key bias and only bound the columns by the block's key count
+            const bool biased = named_bar_or(1, 128, nz);
+            float acc[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
+            float m_run = -INFINITY, l_run = 0.0f;
+            for (int j = 0; j < cur.nkv; ++j, ++it) {
+                const uint32_t ph = it & 1u;
+                uint8_t* p0 = gen + 16384 + (it & 1) * 32768;   // first P atom: over K_j
+                uint8_t* p1 = gen + 5 * 16384;                  // second P atom
+                const int klen = cur.len - j * 128 < 128 ? cur.len - j * 128 : 128;
+                const int n16 = (klen + 15) & ~15;
+                const float* bj = bias_s + j * 128;
+                mbar_wait(s_bar, ph);
+                tc_fence_after();
+                // pass 1: block maximum over the attended keys
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < n16; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0, v);
+                    tmem_ld_wait();
+                    if (!biased && c0 + 32 <= klen) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) mx = fmaxf(mx, __uint_as_float(v[jj]));
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const float bb = bj[c0 + jj];
+                            mx = fmaxf(mx, bb == -INFINITY ? -INFINITY : __uint_as_float(v[jj]) + bb);
+                        }
+                    }
+                }
+                const float m_new = fmaxf(m_run, mx);
+                const float ms = (m_new == -INFINITY ? 0.0f : m_new) * kLog2e;
+                const float corr = m_run == -INFINITY ? 0.0f : fast_exp2(fmaf(m_run, kLog2e, -ms));
+                // pass 2: probabilities relative to the running maximum -> bf16 A operand (two 64-key atoms)
+                float sum = 0.0f;
+                for (int c0 = 0; c0 < n16; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0, v);
+                    tmem_ld_wait();
+                    float e[32];
+                    if (!biased && c0 + 32 <= klen) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            e[jj] = fast_exp2(fmaf(__uint_as_float(v[jj]), kLog2e, -ms));
+                            sum += e[jj];
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const float bb = bj[c0 + jj];
+                            e[jj] = bb == -INFINITY ? 0.0f : fast_exp2(fmaf(__uint_as_float(v[jj]) + bb, kLog2e, -ms));
+                            sum += e[jj];
+                        }
+                    }
+                    if (DROP) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const unsigned long long idx =
+                                (static_cast<unsigned long long>(cur.bh) * p.S_max + (cur.q0 + row)) * p.S_max +
+                                (j * 128 + c0 + jj);
+                            e[jj] = drop_keep(p.drop, idx) ? e[jj] * p.drop.scale : 0.0f;
+                        }
+                    }
+                    uint8_t* pa = c0 < 64 ? p0 : p1;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (c0 + q * 8 >= n16) break;
+                        uint4 o;
+                        o.x = pack_bf16(e[q * 8 + 0], e[q * 8 + 1]);
+                        o.y = pack_bf16(e[q * 8 + 2], e[q * 8 + 3]);
+                        o.z = pack_bf16(e[q * 8 + 4], e[q * 8 + 5]);
+                        o.w = pack_bf16(e[q * 8 + 6], e[q * 8 + 7]);
+                        const int c8 = ((c0 & 63) >> 3) + q;  // 8-key chunk inside the 64-key atom
+                        *reinterpret_cast<uint4*>(pa + row * 128 + ((c8 ^ (row & 7)) << 4)) = o;
+                    }
+                }
+                l_run = fmaf(l_run, corr, sum);
+                m_run = m_new;
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_bar);
+                // O_j back from TMEM into the row's running accumulators
+                mbar_wait(o_bar, ph);
+                tc_fence_after();
+                {
+                    uint32_t o0[32];
+                    tmem_ld32(t_row, o0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], corr, __uint_as_float(o0[i]));
+                    tmem_ld32(t_row + 32, o0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[32 + i] = fmaf(acc[32 + i], corr, __uint_as_float(o0[i]));
+                }
+                tc_fence_before();
+                mbar_arrive(t_bar);
+            }
+            if (row < cur.qlen) {
+                const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(cur.off) + cur.q0 + row) * ldo +
+                                                      cur.h * kHeadDim);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint4 w;
+                    w.x = pack_bf16(acc[q * 8 + 0] * inv, acc[q * 8 + 1] * inv);
+                    w.y = pack_bf16(acc[q * 8 + 2] * inv, acc[q * 8 + 3] * inv);
+                    w.z = pack_bf16(acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv);
+                    w.w = pack_bf16(acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv);
+                    dst[q] = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<128>(tm);
+    }
+}
+
+int encode_qkv_maps(CUtensorMap* maps, const __nv_bfloat16* qkv, int heads, long long rows_alloc, int blocked) {
+    // 3-D view {64 dims, rows, 3*heads column blocks}: token-major rows are 3*heads*64 elements apart
+    // with the blocks side by side; in the blocked layout every block is a contiguous [rows,64] matrix
+    const uint64_t nblk = static_cast<uint64_t>(3) * heads;
+    uint64_t dims[3] = {64, static_cast<uint64_t>(rows_alloc), nblk};
+    uint64_t str_tok[2] = {nblk * 128, 128};
+    uint64_t str_blk[2] = {128, static_cast<uint64_t>(rows_alloc) * 128};
+    for (int i = 0; i < 4; ++i) {
+        uint32_t box[3] = {64, static_cast<uint32_t>(32 * (i + 1)), 1};
+        int rc = encode_tensor_map(&maps[i], qkv, 2, 3, dims, blocked ? str_blk : str_tok, box, 128);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int launch_tc_long(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
+                   int heads, long long rows_alloc, int blocked, __nv_bfloat16* out, cudaStream_t stream,
+                   const DropCfg* drop) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kTcLongSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attention_tc_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kTcLongSmem);
+        if (e != cudaSuccess) {
+            set_last_error("attention_tc_long: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return -static_cast<int>(e);
+        }
+        attr_set = true;
+    }
+    TcLongParams p;
+    const bool dropping = drop != nullptr && drop->thresh != 0u;
+    p.drop = dropping ? *drop : DropCfg{0ull, 0u, 0u, 1.0f};
+    int rc = encode_qkv_maps(p.qkv_map, qkv, heads, rows_alloc, blocked);
+    if (rc) return rc;
+    p.bias = mask_bias;
+    p.seq_off = seq_off;
+    p.out = out;
+    p.S_max = S;
+    p.heads = heads;
+    p.qblocks = (S + 127) / 128;
+    const long long items = static_cast<long long>(B) * heads * p.qblocks;
+    p.items = static_cast<int>(items);
+    const int grid = p.items < 148 * 2 ? p.items : 148 * 2;
+    if (dropping)
+        attention_tc_long_kernel<true><<<grid, kTcThreads, kTcLongSmem, stream>>>(p);
+    else
+        attention_tc_long_kernel<false><<<grid, kTcThreads, kTcLongSmem, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("attention_tc_long_kernel launch: %s", cudaGetErrorString(e));
+        return -static_cast<int>(e);
+    }
+    return 0;
+}
+
 int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B, int S,
               int heads, long long rows_alloc, int blocked, __nv_bfloat16* out, cudaStream_t stream,
               const DropCfg* drop) {
@@ -621,15 +1029,15 @@ int launch_tc(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_o
 
 void attention_set_tc(bool on) { g_attention_tc = on; }
 
-bool attention_prefers_blocked_qkv(int S) { return S <= 128 && g_attention_tc; }
+bool attention_prefers_blocked_qkv(int S) { return S <= kMaxS && g_attention_tc; }
 
 int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const int* seq_off, int B,
                       int S, int heads, __nv_bfloat16* out, cudaStream_t stream, long long rows_alloc,
                       int blocked, const DropCfg* drop) {
     if (B <= 0 || S <= 0) return 0;
     const bool dropping = drop && drop->thresh != 0u;
-    if (blocked && !(S <= 128 && g_attention_tc)) {
-        set_last_error("attention_forward: the blocked qkv layout is only read by the tcgen05 path (S <= 128)");
+    if (blocked && !g_attention_tc) {
+        set_last_error("attention_forward: the blocked qkv layout is only read by the tcgen05 kernels");
         return -1;
     }
     if (S > kMaxS || heads <= 0 || heads > 65535 || B > 65535) {
@@ -643,6 +1051,10 @@ int attention_forward(const __nv_bfloat16* qkv, const float* mask_bias, const in
     if (S <= 128 && g_attention_tc && static_cast<long long>(B) * heads < 0x7fffffffLL)
         return launch_tc(qkv, mask_bias, seq_off, B, S, heads,
                          rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream, drop);
+    // longer sequences: 128-query blocks against key blocks of 128, running softmax, O accumulated in registers
+    if (g_attention_tc && static_cast<long long>(B) * heads * ((S + 127) / 128) < 0x7fffffffLL)
+        return launch_tc_long(qkv, mask_bias, seq_off, B, S, heads,
+                              rows_alloc > 0 ? rows_alloc : static_cast<long long>(B) * S, blocked, out, stream, drop);
     if (dropping) {
         if (S > 64) return launch<128, true>(qkv, mask_bias, seq_off, B, S, heads, out, stream, *drop);
         return launch<64, true>(qkv, mask_bias, seq_off, B, S, heads, out, stream, *drop);

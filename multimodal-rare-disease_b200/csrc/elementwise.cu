@@ -503,6 +503,19 @@ __global__ void pack_conv_bn_kernel(const float* __restrict__ w, const float* __
     if (ci == 0 && s == 0 && rr == 0) bias_out[co] = beta[co] - mean[co] * scale;
 }
 
+__global__ void pack_concat_k_kernel(const __nv_bfloat16* __restrict__ w0, int k0,
+                                     const __nv_bfloat16* __restrict__ w1, int k1,
+                                     const float* __restrict__ b0, const float* __restrict__ b1, int rows,
+                                     __nv_bfloat16* __restrict__ w_out, float* __restrict__ b_out) {
+    const int kt = k0 + k1;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(rows) * kt) return;
+    const int c = static_cast<int>(i % kt);
+    const int r = static_cast<int>(i / kt);
+    w_out[i] = c < k0 ? w0[static_cast<long long>(r) * k0 + c] : w1[static_cast<long long>(r) * k1 + (c - k0)];
+    if (c == 0) b_out[r] = b0[r] + b1[r];
+}
+
 __global__ void pack_stem_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ mean,
                                     const float* __restrict__ var, float eps,
@@ -737,6 +750,13 @@ int pack_conv_bn(const float* w, const float* gamma, const float* beta, const fl
     pack_conv_bn_kernel<<<blocks_for(total, 256), 256, 0, s>>>(w, gamma, beta, mean, var, eps, Cout,
                                                               Cin, k, w_out, bias_out);
     return check_launch("pack_conv_bn");
+}
+
+int pack_concat_k(const __nv_bfloat16* w0, int k0, const __nv_bfloat16* w1, int k1, const float* b0,
+                  const float* b1, int rows, __nv_bfloat16* w_out, float* b_out, cudaStream_t s) {
+    const long long total = static_cast<long long>(rows) * (k0 + k1);
+    pack_concat_k_kernel<<<blocks_for(total, 256), 256, 0, s>>>(w0, k0, w1, k1, b0, b1, rows, w_out, b_out);
+    return check_launch("pack_concat_k");
 }
 
 int pack_stem_bn(const float* w, const float* gamma, const float* beta, const float* mean,

@@ -78,6 +78,10 @@ int fill_f32(float* y, long long n, float v, cudaStream_t s);
 int pack_conv_bn(const float* w, const float* gamma, const float* beta, const float* mean,
                  const float* var, float eps, int Cout, int Cin, int k, __nv_bfloat16* w_out,
                  float* bias_out, cudaStream_t s);
+// w_out[r] = [w0[r][0:k0] | w1[r][0:k1]] (bf16 rows concatenated along K), b_out = b0 + b1: the weights of two 1x1
+// convolutions whose outputs are summed (conv3 + downsample of a bottleneck) as one K-concatenated GEMM.
+int pack_concat_k(const __nv_bfloat16* w0, int k0, const __nv_bfloat16* w1, int k1, const float* b0,
+                  const float* b1, int rows, __nv_bfloat16* w_out, float* b_out, cudaStream_t s);
 // stem weight [64,3,7,7] + BN -> [64][7][32] bf16 (tap row, 8 pixels x 4 channels; unused slots 0)
 int pack_stem_bn(const float* w, const float* gamma, const float* beta, const float* mean,
                  const float* var, float eps, __nv_bfloat16* w_out, float* bias_out,

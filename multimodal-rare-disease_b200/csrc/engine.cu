@@ -56,6 +56,10 @@ struct ConvW {
 struct Bottleneck {
     ConvW c1, c2, c3, ds;
     bool has_ds = false;
+    // conv3 and the downsample branch as one K-concatenated 1x1 convolution: [Cout][c3.cin + ds.cin] bf16, bias
+    // = the two folded BatchNorm shifts added (plan_conv1x1_dual)
+    bf16* c3ds_w = nullptr;
+    float* c3ds_b = nullptr;
 };
 
 struct LinearW {
@@ -75,6 +79,7 @@ struct CnnPlan {
     struct BlockPlan {
         GemmLaunch c1, c2, c3, ds;
         bool has_ds = false;
+        bool fused_ds = false;   // c3 = conv3 + downsample + add (plan_conv1x1_dual); ds is not launched
     };
     std::vector<BlockPlan> blocks;
     const bf16* final_act = nullptr;  // layer4 output [B, H/32*W/32, 2048]
@@ -141,6 +146,7 @@ struct mrd_ctx {
     int fusion_heads = 8;
     int fusion_residual = 1;
     int head_act = MRD_ACT_RELU;
+    int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
     TrainState* train = nullptr;   // training step state (engine_train.cuh), created on first use
@@ -154,6 +160,7 @@ struct mrd_ctx {
     bool load_sync = true;
     RawTable raw;
     Fp32Arena f32_ws;
+    Fp32TrainSave f32_train;   // fp32 check of the training step: saved activations of the text encoder
     Fp32Opts f32_opts() const {
         Fp32Opts o;
         o.bert_heads = bert_heads; o.bert_ln_eps = bert_ln_eps; o.bn_eps = bn_eps;
@@ -391,8 +398,15 @@ int load_cnn(mrd_ctx* c, const Table& t, cudaStream_t s) {
             MRD_TRY(load_conv_bn(c, t, p + "conv2", p + "bn2", stride, &b.c2, s));
             MRD_TRY(load_conv_bn(c, t, p + "conv3", p + "bn3", 1, &b.c3, s));
             b.has_ds = t.find(p + "downsample.0.weight") != nullptr;
-            if (b.has_ds)
+            if (b.has_ds) {
                 MRD_TRY(load_conv_bn(c, t, p + "downsample.0", p + "downsample.1", stride, &b.ds, s));
+                if (b.ds.k == 1 && b.c3.k == 1 && b.ds.cout == b.c3.cout) {
+                    MRD_TRY(walloc(c, &b.c3ds_w, 1LL * b.c3.cout * (b.c3.cin + b.ds.cin)));
+                    MRD_TRY(walloc(c, &b.c3ds_b, b.c3.cout));
+                    MRD_TRY(pack_concat_k(b.c3.w, b.c3.cin, b.ds.w, b.ds.cin, b.c3.b, b.ds.b, b.c3.cout,
+                                          b.c3ds_w, b.c3ds_b, s));
+                }
+            }
         }
     }
     if (bi == 0) {
@@ -652,13 +666,21 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
         }
         const bf16* identity = x;
         bp.has_ds = b.has_ds;
-        if (b.has_ds) {
-            MRD_TRY(plan_conv(&bp.ds, x, B, h, w, b.ds.cin, b.ds.w, b.ds.cout, b.ds.k, b.ds.stride,
-                              b.ds.b, c->dsb, nullptr, ACT_NONE));
-            identity = c->dsb;
+        bp.fused_ds = false;
+        if (b.has_ds && c->fuse_ds && b.c3ds_w) {
+            // conv3 + downsample + add in one accumulator: the downsample output is never written or re-read
+            MRD_TRY(plan_conv1x1_dual(&bp.c3, c->mid1, b.c3.cin, x, b.ds.cin, b.ds.stride, B, ho, wo, b.c3ds_w,
+                                      b.c3.cout, b.c3ds_b, y, ACT_RELU));
+            bp.fused_ds = true;
+        } else {
+            if (b.has_ds) {
+                MRD_TRY(plan_conv(&bp.ds, x, B, h, w, b.ds.cin, b.ds.w, b.ds.cout, b.ds.k, b.ds.stride,
+                                  b.ds.b, c->dsb, nullptr, ACT_NONE));
+                identity = c->dsb;
+            }
+            MRD_TRY(plan_conv(&bp.c3, c->mid1, B, ho, wo, b.c3.cin, b.c3.w, b.c3.cout, b.c3.k, 1,
+                              b.c3.b, y, identity, ACT_RELU));
         }
-        MRD_TRY(plan_conv(&bp.c3, c->mid1, B, ho, wo, b.c3.cin, b.c3.w, b.c3.cout, b.c3.k, 1,
-                          b.c3.b, y, identity, ACT_RELU));
         x = y;
         cur ^= 1;
         h = ho;
@@ -926,6 +948,10 @@ int run_backbone(mrd_ctx* c, const void* images, int img_dtype, int B, int H, in
             MRD_TRY(run(c, c->label(st, ".conv1_1x1"), bp.c1, s));
             MRD_TRY(run(c, c->label(st, c->blocks[i].c2.stride == 2 ? ".conv2_3x3s2" : ".conv2_3x3"),
                         bp.c2, s));
+            if (bp.fused_ds) {
+                MRD_TRY(run(c, c->label(st, ".conv3+downsample"), bp.c3, s));
+                continue;
+            }
             if (bp.has_ds) MRD_TRY(run(c, c->label(st, ".downsample"), bp.ds, s));
             MRD_TRY(run(c, c->label(st, ".conv3_1x1+res"), bp.c3, s));
         }
@@ -1182,6 +1208,7 @@ int mrd_ctx_destroy(mrd_ctx* c) {
     if (c->text_ws.base) cudaFree(c->text_ws.base);
     if (c->batch_ws.base) cudaFree(c->batch_ws.base);
     fp32_arena_free(&c->f32_ws);
+    fp32_arena_free(&c->f32_train.ws);
     train_free(c);
     delete c;
     return 0;
@@ -1209,6 +1236,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fusion_residual") { c->fusion_residual = v != 0.0; c->batch_plans.clear(); }
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
+    else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "load_sync") c->load_sync = v != 0.0;
     else if (k.rfind("train.", 0) == 0) return train_set_option(c, k, v);
     else {
@@ -1446,31 +1474,38 @@ int mrd_ctx_profile_report(mrd_ctx* c, char* buf, int cap) {
     return 0;
 }
 
-int mrd_train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
-                      int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
-                      void* stream) {
+int mrd_train_forward_ex(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
+                         int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
+                         float* feat_map, void* stream) {
     MRD_TRY(check_ctx(c));
     if (B <= 0) return 0;
     if (mask && (mask_dtype < MRD_DT_I64 || mask_dtype > MRD_DT_BF16)) {
         set_last_error("unknown mask dtype code %d", mask_dtype);
         return -1;
     }
-    if (c->fp32_check) {
-        set_last_error("mrd_train_forward: the fp32 check mode covers the inference forward only");
-        return -1;
-    }
-    return train_forward(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits,
+    return train_forward(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, feat_map,
                          static_cast<cudaStream_t>(stream));
 }
 
-int mrd_train_backward(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,
-                       void* stream) {
+int mrd_train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
+                      int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
+                      void* stream) {
+    return mrd_train_forward_ex(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, nullptr, stream);
+}
+
+int mrd_train_backward_ex(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,
+                          float* d_pooled, void* stream) {
     MRD_TRY(check_ctx(c));
     GradTable gt;
     gt.reserve(static_cast<size_t>(n) * 2);
     for (int i = 0; i < n; ++i)
         if (grads[i]) gt.emplace(names[i], grads[i]);
-    return train_backward(c, dlogits, gt, static_cast<cudaStream_t>(stream));
+    return train_backward(c, dlogits, gt, d_pooled, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_train_backward(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,
+                       void* stream) {
+    return mrd_train_backward_ex(c, dlogits, n, names, grads, nullptr, stream);
 }
 
 int mrd_dropout_mask(unsigned long long seed, unsigned int site, double p, long long n, float* out, void* stream) {

@@ -542,10 +542,18 @@ int lin_bwd(mrd_ctx* c, const GradTable& gt, const std::string& name, const floa
     return 0;
 }
 
+int fp32_images_only_train(int img_dtype) {
+    if (img_dtype != MRD_DT_F32) {
+        set_last_error("fp32 check mode takes fp32 images (dtype code %d given)", img_dtype);
+        return -1;
+    }
+    return 0;
+}
+
 // ---- forward -------------------------------------------------------------------------------------
 int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
                   int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
-                  cudaStream_t s) {
+                  float* feat_map, cudaStream_t s) {
     TrainState* t = train_state(c);
     const TrainOpts& o = t->o;
     if (!(c->has_cnn && c->has_text && c->has_fusion && c->has_head)) {
@@ -575,11 +583,37 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     t->ids = ids;
     const int T = B * S;
 
+    if (c->fp32_check) {
+        // fp32 check of the training step: backbone and text encoder in plain fp32 (fp32_check.cu), dropout off;
+        // the batch-level layers below are fp32 in either mode
+        if (o.p_bert_hidden != 0.0 || o.p_bert_attn != 0.0 || o.p_text_out != 0.0 || o.p_cnn_proj != 0.0 ||
+            o.p_fusion != 0.0 || o.p_head != 0.0) {
+            set_last_error("fp32 check (train): every dropout probability must be 0 (the check compares with the "
+                           "reference's autograd, whose Philox masks cannot be reproduced)");
+            return -1;
+        }
+        if (o.bn_train) {
+            set_last_error("fp32 check (train): the frozen backbone must be in eval mode (running statistics)");
+            return -1;
+        }
+        MRD_TRY(fp32_images_only_train(img_dtype));
+        const Fp32Opts fo = c->f32_opts();
+        c->launches += 2;
+        MRD_TRY(fp32_cnn_encoder(c->raw, fo, &c->f32_ws, static_cast<const float*>(images), B, H, W, t->g4, t->pooled,
+                                 feat_map, s));
+        MRD_TRY(fp32_bert_train_forward(c->raw, fo, &c->f32_train, ids, mask, mask_dtype, B, S, t->cls, s));
+    } else {
     // ---- image branch: frozen backbone (forward only), then the trainable projection in fp32
-    if (o.bn_train)
+    if (o.bn_train) {
+        if (feat_map) {
+            set_last_error("training step: the layer4 feature map is exported with the backbone in eval mode only");
+            return -1;
+        }
         MRD_TRY(run_backbone_train(c, images, img_dtype, B, H, W, t->pooled, s));
-    else
-        MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, nullptr, s));
+    } else {
+        MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, t->pooled, feat_map, s));
+    }
+    }
     MRD_TRY(lin_fwd(c, "cnn_encoder.projection.0", t->pooled, c->feat_dim, B, t->a1, c->proj1.out, MRD_ACT_NONE,
                     nullptr, 0, s));
     TRK("train.dropout", CAT_MEM, relu_dropout_f32(t->a1, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->p1, s));
@@ -587,6 +621,7 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
                     nullptr, 0, s));
 
     // ---- text branch
+    if (!c->fp32_check) {
     TRK("train.compact_tokens", CAT_MEM, compact_tokens(mask, mask_dtype, B, S, 0, c->t_seq_off, c->t_row_tok, c->t_bias, c->t_nrows,
                            c->t_scratch, s));
     TRK("train.embed_ln", CAT_MEM, bert_embed_layernorm(ids, B, S, c->word_emb, c->pos_type, c->emb_g, c->emb_b, c->bert_ln_eps, c->vocab,
@@ -613,6 +648,7 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     }
     // CLS row (src/text_encoder.py:118) + TextEncoder.dropout
     TRK("train.cls", CAT_MEM, gather_cls_rows_f32(t->x_final, c->t_seq_off, B, Hd, t->cls, s));
+    }
     TRK("train.dropout", CAT_MEM, dropout_f32(t->cls, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), t->txt, s));
 
     // ---- fusion (src/fusion_model.py:245-291 in train mode)
@@ -669,7 +705,7 @@ int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* d
     return run_f32(c, "train.wgrad", plan, dst, n_in, s);
 }
 
-int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaStream_t s) {
+int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float* d_pooled, cudaStream_t s) {
     TrainState* t = train_state(c);
     if (!t->fwd_done) {
         set_last_error("mrd_train_backward: no forward is pending on this context");
@@ -753,11 +789,19 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, cudaSt
                     c->proj1.out, nullptr, 0, s));
     TRK("train.dropout", CAT_MEM, dropout_f32(t->g0, B, c->proj1.out, make_drop(seed, SITE_CNN_PROJ, o.p_cnn_proj), t->g0, s));
     TRK("train.relu_bwd", CAT_MEM, relu_bwd_f32(t->p1, t->g0, nB * c->proj1.out, t->g0, s));
-    MRD_TRY(lin_bwd(c, gt, "cnn_encoder.projection.0", t->pooled, c->feat_dim, t->g0, c->proj1.out, B, nullptr, 0,
-                    nullptr, 0, s));
+    // d_pooled (optional): gradient of the backbone's pooled output - what Grad-CAM spreads over the layer4 map
+    MRD_TRY(lin_bwd(c, gt, "cnn_encoder.projection.0", t->pooled, c->feat_dim, t->g0, c->proj1.out, B, d_pooled,
+                    c->feat_dim, nullptr, 0, s));
+    bool want_text = false;
+    for (const auto& kv : gt) want_text |= kv.first.rfind("text_encoder.", 0) == 0;
+    if (!want_text) return 0;   // nothing below the text embedding is differentiated (Grad-CAM with a frozen encoder)
 
     // ---- text branch: TextEncoder.dropout, CLS scatter, then the encoder layers in reverse
     TRK("train.dropout", CAT_MEM, dropout_f32(d_txt, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), d_txt, s));
+    if (c->fp32_check) {
+        ++c->launches;
+        return fp32_bert_train_backward(c->raw, c->f32_opts(), &c->f32_train, d_txt, gt, o.pad_idx, s);
+    }
     const size_t nl = c->layers.size();
     bf16* dx_top = (nl & 1) ? t->dxb : t->dxa;   // layer nl-1 reads dx[nl & 1]
     cudaError_t e = cudaMemsetAsync(dx_top, 0, sizeof(bf16) * static_cast<size_t>(T) * Hd, s);

@@ -14,6 +14,7 @@
 #include "elementwise.h"
 #include "simt_gemm.h"
 #include "tma_host.h"
+#include "train_kernels.h"
 
 namespace mrd {
 
@@ -516,6 +517,349 @@ int fp32_head(const RawTable& t, const Fp32Opts& o, Fp32Arena* ws, const float* 
     if (probs) {
         softmax_rows_kernel<<<nblk(B, 128), 128, 0, s>>>(logits, B, C, probs);
         F32_TRY(check_launch("softmax_rows"));
+    }
+    return 0;
+}
+
+// ====================================================================== fp32 check of the training step
+namespace {
+
+__global__ void gelu_f32_kernel(const float* __restrict__ u, long long n, float* __restrict__ g) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = 0.5f * u[i] * (1.0f + erff(u[i] * 0.70710678118654752f));
+}
+// du = dg * gelu'(u), gelu'(u) = Phi(u) + u * phi(u)
+__global__ void gelu_bwd_f32_kernel(const float* __restrict__ u, const float* __restrict__ dg, long long n,
+                                    float* __restrict__ du) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = u[i];
+    du[i] = dg[i] * (0.5f * (1.0f + erff(v * 0.70710678118654752f)) + v * 0.3989422804014327f * expf(-0.5f * v * v));
+}
+
+// dst[b*S*width + c] = src[b*width + c] (dst zeroed): gradient of last_hidden_state[:, 0, :]
+__global__ void scatter_first_rows_kernel(const float* __restrict__ src, int B, long long row_stride, int width,
+                                          float* __restrict__ dst) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * width) return;
+    dst[(i / width) * row_stride + i % width] = src[i];
+}
+
+// Attention backward, pass 1: one warp per (sample, head, query).  Recomputes the probabilities of the row, stores
+// them and dS = P o (dP - rowsum(P o dP)) and produces dQ = scale * dS K.
+__global__ void attention_bwd_q_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ key_bias,
+                                           const float* __restrict__ dctx, int S, int heads, float scale,
+                                           float* __restrict__ P, float* __restrict__ dS,
+                                           float* __restrict__ dqkv) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int q = blockIdx.y * nw + warp;
+    if (q >= S) return;
+    float* pr = sm + warp * (2 * S + 128);
+    float* ds = pr + S;
+    float* qs = ds + S;      // 64
+    float* dos = qs + 64;    // 64
+    const int Hd = heads * 64;
+    const long long row0 = static_cast<long long>(b) * S;
+    const float* qp = qkv + (row0 + q) * 3 * Hd + h * 64;
+    const float* dop = dctx + (row0 + q) * Hd + h * 64;
+    qs[lane] = qp[lane]; qs[lane + 32] = qp[lane + 32];
+    dos[lane] = dop[lane]; dos[lane + 32] = dop[lane + 32];
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+        const float* kp = qkv + (row0 + j) * 3 * Hd + Hd + h * 64;
+        float a = 0.0f;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) a = fmaf(qs[d], kp[d], a);
+        a = a * scale + (key_bias ? key_bias[row0 + j] : 0.0f);
+        pr[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    mx = wmax(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < S; j += 32) {
+        const float e = expf(pr[j] - mx);
+        pr[j] = e;
+        sum += e;
+    }
+    sum = wsum(sum);
+    float delta = 0.0f;
+    for (int j = lane; j < S; j += 32) {
+        const float* vp = qkv + (row0 + j) * 3 * Hd + 2 * Hd + h * 64;
+        float dp = 0.0f;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) dp = fmaf(dos[d], vp[d], dp);
+        const float p = pr[j] / sum;
+        pr[j] = p;
+        ds[j] = dp;
+        delta += p * dp;
+    }
+    delta = wsum(delta);
+    const long long prow = (static_cast<long long>(blockIdx.x) * S + q) * S;
+    for (int j = lane; j < S; j += 32) {
+        const float v = pr[j] * (ds[j] - delta);
+        ds[j] = v;
+        P[prow + j] = pr[j];
+        dS[prow + j] = v;
+    }
+    __syncwarp();
+    float g0 = 0.0f, g1 = 0.0f;
+    for (int j = 0; j < S; ++j) {
+        const float* kp = qkv + (row0 + j) * 3 * Hd + Hd + h * 64;
+        g0 = fmaf(ds[j], kp[lane], g0);
+        g1 = fmaf(ds[j], kp[lane + 32], g1);
+    }
+    float* dq = dqkv + (row0 + q) * 3 * Hd + h * 64;
+    dq[lane] = g0 * scale;
+    dq[lane + 32] = g1 * scale;
+}
+
+// pass 2: one warp per (sample, head, key): dK = scale * dS^T Q, dV = P^T dO
+__global__ void attention_bwd_kv_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                            const float* __restrict__ P, const float* __restrict__ dS, int S,
+                                            int heads, float scale, float* __restrict__ dqkv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int j = blockIdx.y * nw + warp;
+    if (j >= S) return;
+    const int Hd = heads * 64;
+    const long long row0 = static_cast<long long>(b) * S;
+    const long long pbase = static_cast<long long>(blockIdx.x) * S * S;
+    float k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
+    for (int q = 0; q < S; ++q) {
+        const float d = dS[pbase + static_cast<long long>(q) * S + j];
+        const float p = P[pbase + static_cast<long long>(q) * S + j];
+        const float* qp = qkv + (row0 + q) * 3 * Hd + h * 64;
+        const float* dop = dctx + (row0 + q) * Hd + h * 64;
+        k0 = fmaf(d, qp[lane], k0);
+        k1 = fmaf(d, qp[lane + 32], k1);
+        v0 = fmaf(p, dop[lane], v0);
+        v1 = fmaf(p, dop[lane + 32], v1);
+    }
+    float* dk = dqkv + (row0 + j) * 3 * Hd + Hd + h * 64;
+    float* dv = dqkv + (row0 + j) * 3 * Hd + 2 * Hd + h * 64;
+    dk[lane] = k0 * scale;
+    dk[lane + 32] = k1 * scale;
+    dv[lane] = v0;
+    dv[lane + 32] = v1;
+}
+
+// scatter-add of the embedding-sum gradient into the three tables (nn.Embedding backward; the word row of
+// padding_idx receives nothing, HF:models/bert/modeling_bert.py:76)
+__global__ void embed_bwd_f32_kernel(const long long* __restrict__ ids, const float* __restrict__ de, int S,
+                                     int Hd, int vocab, int pad_idx, long long total, float* __restrict__ dword,
+                                     float* __restrict__ dpos, float* __restrict__ dtype0) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int hh = static_cast<int>(i % Hd);
+    const long long tok = i / Hd;
+    const int j = static_cast<int>(tok % S);
+    long long id = ids[tok];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    const float v = de[i];
+    if (v == 0.0f) return;
+    if (dword && id != pad_idx) atomicAdd(dword + id * Hd + hh, v);
+    if (dpos) atomicAdd(dpos + static_cast<long long>(j) * Hd + hh, v);
+    if (dtype0) atomicAdd(dtype0 + hh, v);
+}
+
+// C[M,N] (+)= A * B^T with arbitrary element strides; one CTA per output element group (no split-K atomics)
+int gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs, long long b_cs, int M,
+             int N, int K, float* C, long long ldc, int accumulate, const float* res, long long ldr, cudaStream_t s) {
+    SimtGemm g;
+    g.A = A; g.a_rs = a_rs; g.a_cs = a_cs;
+    g.B = B; g.b_rs = b_rs; g.b_cs = b_cs;
+    g.M = M; g.N = N; g.K = K;
+    g.C = C; g.ldc = ldc;
+    g.accumulate = accumulate;
+    g.res = res; g.ldr = ldr;
+    g.ksplit = 1;
+    return simt_gemm(g, s);
+}
+
+inline float* grad_of(const Fp32GradTable& g, const std::string& k) {
+    auto it = g.find(k);
+    return it == g.end() ? nullptr : it->second;
+}
+
+// y = x W^T + b: dW += dy^T x, db += colsum(dy), dx = dy W (+ dx_res) when dx != null
+int linear_bwd(const RawTable& t, const Fp32GradTable& gt, const std::string& name, const float* x, long long ldx,
+               const float* dy, long long lddy, int M, float* dx, long long lddx, const float* dx_res,
+               long long ld_res, cudaStream_t s) {
+    const RawTensor* w;
+    F32_TRY(need(t, name + ".weight", &w));
+    const int N = static_cast<int>(w->d[0]), K = static_cast<int>(w->d[1]);
+    if (float* gw = grad_of(gt, name + ".weight"))
+        F32_TRY(gemm_f32(dy, 1, lddy, x, 1, ldx, N, K, M, gw, K, 1, nullptr, 0, s));
+    if (float* gb = grad_of(gt, name + ".bias")) F32_TRY(colsum_f32(dy, lddy, M, N, gb, s));
+    if (dx) F32_TRY(gemm_f32(dy, lddy, 1, w->p, 1, K, M, K, N, dx, lddx, 0, dx_res, ld_res, s));
+    return 0;
+}
+
+}  // namespace
+
+int fp32_bert_train_forward(const RawTable& t, const Fp32Opts& o, Fp32TrainSave* sv, const long long* ids,
+                            const void* mask, int mask_dtype, int B, int S, float* cls, cudaStream_t s) {
+    sv->valid = false;
+    const std::string e = "text_encoder.encoder.embeddings.";
+    const RawTensor *we, *pe, *te, *wf;
+    F32_TRY(need(t, e + "word_embeddings.weight", &we));
+    F32_TRY(need(t, e + "position_embeddings.weight", &pe));
+    F32_TRY(need(t, e + "token_type_embeddings.weight", &te));
+    F32_TRY(need(t, "text_encoder.encoder.encoder.layer.0.intermediate.dense.weight", &wf));
+    const int Hd = static_cast<int>(we->d[1]), vocab = static_cast<int>(we->d[0]);
+    const int F = static_cast<int>(wf->d[0]), heads = o.bert_heads;
+    int L = 0;
+    while (L < 48 && t.find("text_encoder.encoder.encoder.layer." + std::to_string(L) + ".attention.self.query.weight") != t.end())
+        ++L;
+    if (Hd != heads * 64 || S > pe->d[0] || S <= 0 || S > 512 || L == 0) {
+        set_last_error("fp32 check (train): text encoder shape unsupported (hidden %d, heads %d, S %d, layers %d)", Hd,
+                       heads, S, L);
+        return -1;
+    }
+    const long long T = 1LL * B * S;
+    const long long att = 1LL * B * heads * S * S;
+    const size_t per_layer = 6 * pad256(T * Hd) + pad256(T * 3 * Hd) + 2 * pad256(T * F);   // x ctx s1 h1 s2 (+1 spare), qkv, u g
+    const size_t total = L * per_layer + pad256(T) + 2 * pad256(T * Hd) /* emb_sum, x_final */ +
+                         5 * pad256(T * Hd) + pad256(T * F) + pad256(T * 3 * Hd) + 2 * pad256(att);
+    F32_TRY(arena_prepare(&sv->ws, total, s));
+    sv->B = B; sv->S = S; sv->Hd = Hd; sv->F = F; sv->L = L; sv->ids = ids;
+    sv->bias = take(&sv->ws, T);
+    sv->emb_sum = take(&sv->ws, T * Hd);
+    sv->x_final = take(&sv->ws, T * Hd);
+    for (int i = 0; i < L; ++i) {
+        sv->x[i] = take(&sv->ws, T * Hd);
+        sv->qkv[i] = take(&sv->ws, T * 3 * Hd);
+        sv->ctx[i] = take(&sv->ws, T * Hd);
+        sv->s1[i] = take(&sv->ws, T * Hd);
+        sv->h1[i] = take(&sv->ws, T * Hd);
+        sv->u[i] = take(&sv->ws, T * F);
+        sv->g[i] = take(&sv->ws, T * F);
+        sv->s2[i] = take(&sv->ws, T * Hd);
+    }
+    sv->dxa = take(&sv->ws, T * Hd);
+    sv->dxb = take(&sv->ws, T * Hd);
+    sv->d_s = take(&sv->ws, T * Hd);
+    sv->d_h1 = take(&sv->ws, T * Hd);
+    sv->d_ctx = take(&sv->ws, T * Hd);
+    sv->d_big = take(&sv->ws, T * F);
+    sv->d_qkv = take(&sv->ws, T * 3 * Hd);
+    sv->P = take(&sv->ws, att);
+    sv->dS = take(&sv->ws, att);
+
+    const int Ti = static_cast<int>(T);
+    if (mask) F32_TRY(mask_to_bias(mask, mask_dtype, B, S, sv->bias, s));
+    const float* kb = mask ? sv->bias : nullptr;
+    sv->has_mask = mask != nullptr;
+    embed_sum_kernel<<<nblk(T * Hd, 256), 256, 0, s>>>(ids, we->p, pe->p, te->p, S, Hd, vocab, T * Hd, sv->emb_sum);
+    F32_TRY(check_launch("embed_sum"));
+    F32_TRY(layernorm(t, e + "LayerNorm", sv->emb_sum, Hd, nullptr, 0, o.bert_ln_eps, Ti, Hd, sv->x[0], Hd, s));
+    const int nw = 4;
+    for (int i = 0; i < L; ++i) {
+        const std::string p = "text_encoder.encoder.encoder.layer." + std::to_string(i) + ".";
+        float* x_next = i + 1 < L ? sv->x[i + 1] : sv->x_final;
+        F32_TRY(linear(t, p + "attention.self.query", sv->x[i], Hd, Ti, sv->qkv[i], 3 * Hd, MRD_ACT_NONE, nullptr, 0, s));
+        F32_TRY(linear(t, p + "attention.self.key", sv->x[i], Hd, Ti, sv->qkv[i] + Hd, 3 * Hd, MRD_ACT_NONE, nullptr, 0, s));
+        F32_TRY(linear(t, p + "attention.self.value", sv->x[i], Hd, Ti, sv->qkv[i] + 2 * Hd, 3 * Hd, MRD_ACT_NONE, nullptr, 0, s));
+        attention_f32_kernel<<<dim3(B * heads, (S + nw - 1) / nw), nw * 32, nw * (S + 64) * sizeof(float), s>>>(
+            sv->qkv[i], kb, S, heads, 0.125f, sv->ctx[i]);
+        F32_TRY(check_launch("attention_f32"));
+        // s1 = dense(ctx) + x ; h1 = LayerNorm(s1)   (HF:294-298)
+        F32_TRY(linear(t, p + "attention.output.dense", sv->ctx[i], Hd, Ti, sv->s1[i], Hd, MRD_ACT_NONE, sv->x[i], Hd, s));
+        F32_TRY(layernorm(t, p + "attention.output.LayerNorm", sv->s1[i], Hd, nullptr, 0, o.bert_ln_eps, Ti, Hd,
+                          sv->h1[i], Hd, s));
+        // u = dense(h1) ; g = gelu(u) ; s2 = dense(g) + h1 ; x' = LayerNorm(s2)   (HF:339-356)
+        F32_TRY(linear(t, p + "intermediate.dense", sv->h1[i], Hd, Ti, sv->u[i], F, MRD_ACT_NONE, nullptr, 0, s));
+        gelu_f32_kernel<<<nblk(T * F, 256), 256, 0, s>>>(sv->u[i], T * F, sv->g[i]);
+        F32_TRY(check_launch("gelu_f32"));
+        F32_TRY(linear(t, p + "output.dense", sv->g[i], F, Ti, sv->s2[i], Hd, MRD_ACT_NONE, sv->h1[i], Hd, s));
+        F32_TRY(layernorm(t, p + "output.LayerNorm", sv->s2[i], Hd, nullptr, 0, o.bert_ln_eps, Ti, Hd, x_next, Hd, s));
+    }
+    gather_rows_kernel<<<nblk(1LL * B * Hd, 256), 256, 0, s>>>(sv->x_final, 1LL * S * Hd, B, Hd, cls);
+    F32_TRY(check_launch("gather_rows"));
+    sv->valid = true;
+    return 0;
+}
+
+int fp32_bert_train_backward(const RawTable& t, const Fp32Opts& o, Fp32TrainSave* sv, const float* d_cls,
+                             const Fp32GradTable& gt, int pad_idx, cudaStream_t s) {
+    if (!sv->valid) {
+        set_last_error("fp32 check (train): no forward is pending");
+        return -1;
+    }
+    sv->valid = false;
+    const int B = sv->B, S = sv->S, Hd = sv->Hd, F = sv->F, L = sv->L, heads = o.bert_heads;
+    const long long T = 1LL * B * S;
+    const int Ti = static_cast<int>(T);
+    const float* kb = sv->has_mask ? sv->bias : nullptr;
+    auto get = [&](const std::string& k) -> const float* {
+        auto it = t.find(k);
+        return it == t.end() ? nullptr : it->second.p;
+    };
+    float* dx_in = (L & 1) ? sv->dxb : sv->dxa;   // layer i reads dx[(i+1)&1], writes dx[i&1]
+    cudaError_t ce = cudaMemsetAsync(dx_in, 0, sizeof(float) * T * Hd, s);
+    if (ce != cudaSuccess) {
+        set_last_error("fp32 check (train): memset: %s", cudaGetErrorString(ce));
+        return -static_cast<int>(ce);
+    }
+    scatter_first_rows_kernel<<<nblk(1LL * B * Hd, 256), 256, 0, s>>>(d_cls, B, 1LL * S * Hd, Hd, dx_in);
+    F32_TRY(check_launch("scatter_first_rows"));
+    const int nw = 4;
+    for (int i = L - 1; i >= 0; --i) {
+        const std::string p = "text_encoder.encoder.encoder.layer." + std::to_string(i) + ".";
+        const float* dxi = ((i + 1) & 1) ? sv->dxb : sv->dxa;
+        float* dxo = (i & 1) ? sv->dxb : sv->dxa;
+        const float* g2 = get(p + "output.LayerNorm.weight");
+        const float* g1 = get(p + "attention.output.LayerNorm.weight");
+        if (!g1 || !g2) {
+            set_last_error("fp32 check (train): LayerNorm weights of layer %d missing", i);
+            return -2;
+        }
+        // x' = LN2(s2), s2 = h1 + W2 g + b2
+        F32_TRY(ln_bwd_f32(sv->s2[i], Hd, dxi, Hd, g2, o.bert_ln_eps, Ti, Hd, sv->d_s, Hd,
+                           grad_of(gt, p + "output.LayerNorm.weight"), grad_of(gt, p + "output.LayerNorm.bias"), s));
+        F32_TRY(linear_bwd(t, gt, p + "output.dense", sv->g[i], F, sv->d_s, Hd, Ti, sv->d_big, F, nullptr, 0, s));
+        gelu_bwd_f32_kernel<<<nblk(T * F, 256), 256, 0, s>>>(sv->u[i], sv->d_big, T * F, sv->d_big);
+        F32_TRY(check_launch("gelu_bwd_f32"));
+        // dh1 = du W1 + d_s2 (residual path)
+        F32_TRY(linear_bwd(t, gt, p + "intermediate.dense", sv->h1[i], Hd, sv->d_big, F, Ti, sv->d_h1, Hd, sv->d_s, Hd, s));
+        // h1 = LN1(s1), s1 = x + Wo ctx + bo
+        F32_TRY(ln_bwd_f32(sv->s1[i], Hd, sv->d_h1, Hd, g1, o.bert_ln_eps, Ti, Hd, sv->d_s, Hd,
+                           grad_of(gt, p + "attention.output.LayerNorm.weight"),
+                           grad_of(gt, p + "attention.output.LayerNorm.bias"), s));
+        F32_TRY(linear_bwd(t, gt, p + "attention.output.dense", sv->ctx[i], Hd, sv->d_s, Hd, Ti, sv->d_ctx, Hd, nullptr, 0, s));
+        attention_bwd_q_f32_kernel<<<dim3(B * heads, (S + nw - 1) / nw), nw * 32, nw * (2 * S + 128) * sizeof(float), s>>>(
+            sv->qkv[i], kb, sv->d_ctx, S, heads, 0.125f, sv->P, sv->dS, sv->d_qkv);
+        F32_TRY(check_launch("attention_bwd_q_f32"));
+        attention_bwd_kv_f32_kernel<<<dim3(B * heads, (S + nw - 1) / nw), nw * 32, 0, s>>>(
+            sv->qkv[i], sv->d_ctx, sv->P, sv->dS, S, heads, 0.125f, sv->d_qkv);
+        F32_TRY(check_launch("attention_bwd_kv_f32"));
+        // dx = dq Wq + dk Wk + dv Wv + d_s1
+        F32_TRY(linear_bwd(t, gt, p + "attention.self.query", sv->x[i], Hd, sv->d_qkv, 3 * Hd, Ti, dxo, Hd, sv->d_s, Hd, s));
+        F32_TRY(linear_bwd(t, gt, p + "attention.self.key", sv->x[i], Hd, sv->d_qkv + Hd, 3 * Hd, Ti, sv->d_h1, Hd, dxo, Hd, s));
+        F32_TRY(linear_bwd(t, gt, p + "attention.self.value", sv->x[i], Hd, sv->d_qkv + 2 * Hd, 3 * Hd, Ti, dxo, Hd, sv->d_h1, Hd, s));
+    }
+    // embeddings: x0 = LayerNorm(word[id] + position[j] + token_type[0])
+    const std::string e = "text_encoder.encoder.embeddings.";
+    const float* ge = get(e + "LayerNorm.weight");
+    const RawTensor* we;
+    F32_TRY(need(t, e + "word_embeddings.weight", &we));
+    if (!ge) {
+        set_last_error("fp32 check (train): embedding LayerNorm weight missing");
+        return -2;
+    }
+    F32_TRY(ln_bwd_f32(sv->emb_sum, Hd, sv->dxa, Hd, ge, o.bert_ln_eps, Ti, Hd, sv->d_s, Hd,
+                       grad_of(gt, e + "LayerNorm.weight"), grad_of(gt, e + "LayerNorm.bias"), s));
+    float* gw = grad_of(gt, e + "word_embeddings.weight");
+    float* gp = grad_of(gt, e + "position_embeddings.weight");
+    float* gty = grad_of(gt, e + "token_type_embeddings.weight");
+    if (gw || gp || gty) {
+        embed_bwd_f32_kernel<<<nblk(T * Hd, 256), 256, 0, s>>>(sv->ids, sv->d_s, S, Hd, static_cast<int>(we->d[0]),
+                                                               pad_idx, T * Hd, gw, gp, gty);
+        F32_TRY(check_launch("embed_bwd_f32"));
     }
     return 0;
 }

@@ -154,7 +154,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     constexpr int NSUB = BLOCK_N / 64;
-    int num_k = p.num_taps * p.kc_per_tap;
+    int num_k = p.kc_split ? p.num_k_total : p.num_taps * p.kc_per_tap;
     if constexpr (SPLITK) {
         if (p.dyn_k) {   // token-packed contraction (weight gradients): only the live K blocks
             int live_k = (__ldg(p.dyn_k) + C::BLOCK_K - 1) / C::BLOCK_K;
@@ -319,8 +319,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t a_dst = a_smem + stage * C::A_STAGE;
                     const uint32_t b_dst = b_smem + stage * C::B_STAGE;
-                    const int tap = ks / p.kc_per_tap;
-                    const int kc = ks - tap * p.kc_per_tap;
+                    // K-concatenated pair of 1x1 convolutions: chunks [0, kc_split) read taps[0], the rest taps[1]
+                    const int tap = p.kc_split ? (ks >= p.kc_split ? 1 : 0) : ks / p.kc_per_tap;
+                    const int kc = ks - tap * (p.kc_split ? p.kc_split : p.kc_per_tap);
                     const TapDesc td = p.taps[tap];
                     tma_load_4d(&p.a_map[td.map], full_bar(stage), a_dst, kc * C::BLOCK_K,
                                 t.w0 + td.dw, t.h0 + td.dh, t.n0);
@@ -870,6 +871,103 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
             rc = encode_tensor_map(&p.r_map, residual, 2, 4, dims, str, box, 128);
             if (rc) return rc;
         }
+    }
+    return finish_plan(g, bn);
+}
+
+int plan_conv1x1_dual(GemmLaunch* g, const __nv_bfloat16* X0, int C0, const __nv_bfloat16* X1, int C1,
+                      int stride1, int N, int Ho, int Wo, const __nv_bfloat16* Wcat, int Cout,
+                      const float* bias, __nv_bfloat16* Y, int act) {
+    memset(g, 0, sizeof(*g));
+    if (C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0 || (stride1 != 1 && stride1 != 2) || N <= 0 || Ho <= 0 ||
+        Wo <= 0) {
+        set_last_error("plan_conv1x1_dual: unsupported shape C0=%d C1=%d Cout=%d stride=%d", C0, C1, Cout, stride1);
+        return -1;
+    }
+    ConvGemmParams& p = g->p;
+    const long long M = static_cast<long long>(N) * Ho * Wo;
+    if (M > 0x7fffffffLL) {
+        set_last_error("plan_conv1x1_dual: M too large");
+        return -1;
+    }
+    p.bias = bias;
+    p.has_res = 0;
+    p.num_taps = 2;
+    p.kc_per_tap = C0 / 64;
+    p.kc_split = C0 / 64;
+    p.num_k_total = (C0 + C1) / 64;
+    p.taps[0] = TapDesc{0, 0, 0, 0};
+    p.taps[1] = TapDesc{1, 0, 0, 0};
+    p.Cout = Cout;
+    p.act = act;
+    p.store_bf16 = 1;
+    g->flops = 2.0 * M * static_cast<double>(Cout) * (C0 + C1);
+    g->bytes = 2.0 * (1.0 * M * C0 + 1.0 * M * C1 + 1.0 * Cout * (C0 + C1) + 1.0 * M * Cout);
+    if (stride1 == 1) {
+        // both operands are plain [M, C] matrices: flat 128-row tiles as in plan_gemm
+        p.tw = 128; p.th = 1; p.nb = 1;
+        p.tiles_w = static_cast<int>((M + 127) / 128); p.tiles_h = 1; p.tiles_img = 1;
+        p.Wo = static_cast<int>(M); p.Ho = 1; p.Nimg = 1;
+        const __nv_bfloat16* xs[2] = {X0, X1};
+        const int cs[2] = {C0, C1};
+        for (int i = 0; i < 2; ++i) {
+            uint64_t dims[4] = {(uint64_t)cs[i], (uint64_t)M, 1, 1};
+            uint64_t str[3] = {(uint64_t)cs[i] * 2, (uint64_t)cs[i] * 2 * M, (uint64_t)cs[i] * 2 * M};
+            uint32_t box[4] = {64, 128, 1, 1};
+            int rc = encode_tensor_map(&p.a_map[i], xs[i], 2, 4, dims, str, box, 128);
+            if (rc) return rc;
+        }
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)M, 1, 1};
+        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Cout * 2 * M, (uint64_t)Cout * 2 * M};
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    } else {
+        // X1 is read at every second row / column: tiles are boxes of output pixels (as in plan_conv)
+        p.Wo = Wo; p.Ho = Ho; p.Nimg = N;
+        p.tw = Wo < 128 ? Wo : 128;
+        p.th = 128 / p.tw;
+        if (p.th > Ho) p.th = Ho;
+        if (p.th < 1) p.th = 1;
+        p.nb = 1;
+        if (p.th == Ho && p.tw == Wo) {
+            p.nb = 128 / (p.tw * p.th);
+            if (p.nb < 1) p.nb = 1;
+            if (p.nb > N) p.nb = N;
+        }
+        p.tiles_w = (Wo + p.tw - 1) / p.tw;
+        p.tiles_h = (Ho + p.th - 1) / p.th;
+        p.tiles_img = (N + p.nb - 1) / p.nb;
+        const int H = Ho * 2, W = Wo * 2;
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.nb};
+        {
+            uint64_t dims[4] = {(uint64_t)C0, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+            uint64_t str[3] = {(uint64_t)C0 * 2, (uint64_t)Wo * C0 * 2, (uint64_t)Ho * Wo * C0 * 2};
+            int rc = encode_tensor_map(&p.a_map[0], X0, 2, 4, dims, str, box, 128);
+            if (rc) return rc;
+        }
+        {
+            uint64_t dims[4] = {(uint64_t)C1, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+            uint64_t str[3] = {(uint64_t)2 * C1 * 2, (uint64_t)2 * W * C1 * 2, (uint64_t)H * W * C1 * 2};
+            int rc = encode_tensor_map(&p.a_map[1], X1, 2, 4, dims, str, box, 128);
+            if (rc) return rc;
+        }
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+        int rc = encode_tensor_map(&p.c_map, Y, 2, 4, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    p.a_map[2] = p.a_map[3] = p.a_map[0];
+    p.r_map = p.c_map;  // never dereferenced (has_res == 0)
+    const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_img;
+    const int bn = pick_block_n(Cout, m_tiles, gemm_num_sms());
+    {
+        const uint64_t Kt = static_cast<uint64_t>(C0 + C1);
+        uint64_t dims[2] = {Kt, (uint64_t)Cout};
+        uint64_t str[1] = {Kt * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = encode_tensor_map(&p.b_map, Wcat, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
     }
     return finish_plan(g, bn);
 }

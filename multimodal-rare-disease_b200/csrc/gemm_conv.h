@@ -53,6 +53,11 @@ struct alignas(64) ConvGemmParams {
     int ksplit;
     int f32_accum;
     const int* dyn_k;
+    // K-concatenated 1x1 convolutions (plan_conv1x1_dual: conv3 + downsample of a bottleneck's first block summed in
+    // one accumulator): K chunks [0, kc_split) come from taps[0], the rest from taps[1]; 0 = every tap has
+    // kc_per_tap chunks.  num_k_total = total K chunks in that mode.
+    int kc_split;
+    int num_k_total;
 };
 
 struct GemmLaunch {
@@ -81,6 +86,15 @@ int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int
 int plan_conv(GemmLaunch* out, const __nv_bfloat16* X, int N, int H, int W, int Cin,
               const __nv_bfloat16* Wt, int Cout, int ksize, int stride, const float* bias,
               __nv_bfloat16* Y, const __nv_bfloat16* residual, int act, int out_pad = 0);
+
+// Two 1x1 convolutions summed into one output: Y = act(X0 * W[:, :C0]^T + subsample_s(X1) * W[:, C0:]^T + bias).
+// X0: [N,Ho,Wo,C0] (the bottleneck's conv2 output), X1: [N,Ho*s,Wo*s,C1] read at stride s in {1,2} (the block
+// input), Wcat: [Cout][C0+C1] bf16, bias = the two folded BatchNorm shifts added.  This is conv3 + downsample +
+// residual add of a bottleneck's first block (TV:models/resnet.py:143-163 with a downsample branch) as ONE GEMM
+// over the concatenated K, so the downsample output never exists in memory.
+int plan_conv1x1_dual(GemmLaunch* out, const __nv_bfloat16* X0, int C0, const __nv_bfloat16* X1, int C1,
+                      int stride1, int N, int Ho, int Wo, const __nv_bfloat16* Wcat, int Cout,
+                      const float* bias, __nv_bfloat16* Y, int act);
 
 // 3x3 stride-1 pad-1 convolution in flat-shift mode.  Xpad: zero-bordered [N][H+2][W+2][Cin] bf16;
 // Wt: [Cout][3][3][Cin]; Y: [N,H,W,Cout] (unpadded).  The halo span of a tile is loaded once per

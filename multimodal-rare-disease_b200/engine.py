@@ -297,27 +297,31 @@ class Engine:
         return logits, probs, img_e, txt_e, fused, a1, a2
 
     # ------------------------------------------------------------------ training step
-    def train_forward(self, images, input_ids, attention_mask, num_classes: int, seed: int) -> torch.Tensor:
-        """Train-mode forward (dropout active, activations kept inside the context) -> logits f32 [B,C]."""
+    def train_forward(self, images, input_ids, attention_mask, num_classes: int, seed: int,
+                      want_map: bool = False):
+        """Train-mode forward (dropout active, activations kept inside the context) -> logits f32 [B,C]
+        (and, with want_map, the layer4 feature map f32 [B,2048,H/32,W/32] of this forward)."""
         images, icode = self._images(images)
         ids, mask, mcode = self._text(input_ids, attention_mask)
         B, _, H, W = images.shape
         if ids.shape[0] != B:
             raise ValueError(f"batch mismatch: {B} images vs {ids.shape[0]} token rows")
         logits = self._f32(B, num_classes)
+        fmap = self._f32(B, 2048, H // 32, W // 32) if want_map else None
         self._train_inputs = (images, ids, mask)   # the backward re-reads the ids
         self.train_serial = getattr(self, "train_serial", 0) + 1
         if B:
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.mrd_train_forward(
+                _lib.check(self.lib.mrd_train_forward_ex(
                     self._ctx, images.data_ptr(), icode, ids.data_ptr(), _ptr(mask), mcode, B, H, W,
-                    ids.shape[1], C.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), logits.data_ptr(),
+                    ids.shape[1], C.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), logits.data_ptr(), _ptr(fmap),
                     _stream(self.device)), "mrd_train_forward")
-        return logits
+        return (logits, fmap) if want_map else logits
 
-    def train_backward(self, dlogits: torch.Tensor, named_shapes) -> list:
+    def train_backward(self, dlogits: torch.Tensor, named_shapes, want_dpooled: bool = False):
         """named_shapes: [(canonical state_dict name, shape)] of the parameters that want a gradient.
-        Returns their f32 gradients as views of ONE flat buffer (a single all-reduce bucket)."""
+        Returns their f32 gradients as views of ONE flat buffer (a single all-reduce bucket); with want_dpooled
+        also d(loss)/d(pooled backbone features) f32 [B,2048]."""
         dl = dlogits.to(self.device, torch.float32).contiguous()
         sizes = [int(torch.Size(sh).numel()) for _, sh in named_shapes]
         offs, tot = [], 0
@@ -334,10 +338,11 @@ class Engine:
             views.append(v)
             names[i] = name.encode()
             ptrs[i] = v.data_ptr()
+        d_pooled = torch.zeros(dl.shape[0], 2048, dtype=torch.float32, device=self.device) if want_dpooled else None
         if dl.shape[0]:
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.mrd_train_backward(self._ctx, dl.data_ptr(), n, names, ptrs,
-                                                       _stream(self.device)), "mrd_train_backward")
+                _lib.check(self.lib.mrd_train_backward_ex(self._ctx, dl.data_ptr(), n, names, ptrs, _ptr(d_pooled),
+                                                          _stream(self.device)), "mrd_train_backward")
         self._train_inputs = None
         self.last_flat_grad = flat
-        return views
+        return (views, d_pooled) if want_dpooled else views

@@ -32,8 +32,19 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eng, images, input_ids, attention_mask, seed, named_shapes, ddp, *params):
+        """ddp = (num_classes, data_parallel, process_group, hooked): hooked = the backbone module whose
+        forward / backward hooks are served (Grad-CAM on cnn_encoder.get_attention_layer()) or None."""
         ctx.eng, ctx.named_shapes, ctx.ddp = eng, named_shapes, ddp
-        logits = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
+        ctx.hooked = ddp[3] if len(ddp) > 3 else None
+        if ctx.hooked is None:
+            logits = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
+        else:
+            logits, fmap = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed, want_map=True)
+            ctx.map_shape = tuple(fmap.shape)
+            # forward hooks of the hooked module see its output as the reference's would (NCHW fp32); the module's
+            # input (layer3's output) is not materialised in that layout: hooks get an empty input tuple
+            for hook in list(ctx.hooked._forward_hooks.values()):
+                hook(ctx.hooked, (), fmap)
         ctx.serial = eng.train_serial
         return logits
 
@@ -44,7 +55,16 @@ class _TrainStep(torch.autograd.Function):
                 "backward through a train-mode forward whose saved activations were overwritten by a newer "
                 "train-mode forward of the same model: the B200 training step keeps ONE forward pending "
                 "(call backward before the next forward, as the reference's loops do)")
-        grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
+        if ctx.hooked is not None:
+            grads, d_pooled = ctx.eng.train_backward(dlogits, ctx.named_shapes, want_dpooled=True)
+            # AdaptiveAvgPool2d(1) backward (TV:models/resnet.py:278): every position of the layer4 map receives
+            # d_pooled / (h*w); that is grad_output of the hooked module
+            Bn, Cn, h, w = ctx.map_shape
+            d_map = (d_pooled / float(h * w)).view(Bn, Cn, 1, 1).expand(Bn, Cn, h, w).contiguous()
+            for hook in list(ctx.hooked._backward_hooks.values()):
+                hook(ctx.hooked, (None,), (d_map,))
+        else:
+            grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
         if ctx.ddp[1]:
             # data parallel: every gradient of the step lives in one flat buffer -> one all-reduce
             from .parallel import allreduce_mean_
@@ -137,6 +157,12 @@ class MultimodalClassifier(B200Module):
         self.text_encoder._check()
         if self.training:
             return self._forward_train(images, input_ids, attention_mask, return_embeddings)
+        if not return_embeddings:
+            hooked = self._hooked_attention_layer()
+            if hooked is not None:
+                # Grad-CAM (notebooks/explainability.ipynb cell 3): hooks on cnn_encoder.get_attention_layer() and
+                # logits[0, c].backward() under model.eval() - the eval-mode forward made differentiable
+                return self._forward_train(images, input_ids, attention_mask, False, explain=hooked)
         logits, probs, img_e, txt_e, fused, a1, a2 = self._engine().multimodal(
             images, input_ids, attention_mask, self._dims(), want_embeddings=return_embeddings,
             logits_out=logits_out)
@@ -149,6 +175,15 @@ class MultimodalClassifier(B200Module):
         return out
 
     # ---- training step ------------------------------------------------------------------------
+    def _hooked_attention_layer(self):
+        """cnn_encoder.get_attention_layer() (backbone.layer4, src/cnn_encoder.py:186-198) when somebody registered
+        forward or backward hooks on it, else None."""
+        try:
+            m = self.cnn_encoder.get_attention_layer()
+        except Exception:
+            return None
+        return m if (len(m._forward_hooks) or len(m._backward_hooks)) else None
+
     def _train_options(self) -> Dict[str, float]:
         mc = self.text_encoder.model_config
         bn_train = any(m.training for m in self.cnn_encoder.backbone.modules()
@@ -180,9 +215,11 @@ class MultimodalClassifier(B200Module):
             out.append((name, p))
         return out
 
-    def _forward_train(self, images, input_ids, attention_mask, return_embeddings):
+    def _forward_train(self, images, input_ids, attention_mask, return_embeddings, explain=None):
         """Train-mode forward on the B200 path, differentiable through torch.autograd: the reference's
-        training loops (src/train.py:247-333, src/train_multimodal.py:508-556) run unchanged."""
+        training loops (src/train.py:247-333, src/train_multimodal.py:508-556) run unchanged.
+        explain = a hooked backbone module: the same machinery in EVAL semantics (no dropout, BatchNorm on running
+        statistics) with the module's hooks served - what Grad-CAM needs."""
         if return_embeddings:
             raise NotImplementedError("return_embeddings=True is an inference-path feature (eval mode)")
         p_att = {self.fusion.fusion_layer.image_to_text_attention.dropout.p,
@@ -192,6 +229,8 @@ class MultimodalClassifier(B200Module):
             raise NotImplementedError("the fusion dropouts must share one probability (FusionConfig.dropout)")
         eng = self._engine(allow_training=True)
         opts = self._train_options()
+        if explain is not None:
+            opts = {k: (v if k == "train.pad_idx" else 0.0) for k, v in opts.items()}
         if eng.train_opts != opts:
             # the cache of what was applied lives on the Engine: a new engine (model.to(other device), deepcopy,
             # unpickling) starts from the library defaults and gets every option again
@@ -202,7 +241,11 @@ class MultimodalClassifier(B200Module):
             eng.set_option("load_sync", 0.0)
             eng.train_opts = dict(opts)
         named = self._trainable()
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
+        if explain is not None and not named:
+            raise RuntimeError("every parameter is frozen: logits.backward() has nothing to differentiate (the "
+                               "reference raises here as well unless the input requires grad)")
+        # eval semantics draw nothing from the generator (no dropout): leave torch's RNG stream untouched
+        seed = 0 if explain is not None else int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: follows torch.manual_seed
         shapes = tuple((n, tuple(p.shape)) for n, p in named)
         ddp = self.__dict__.get("_mrd_ddp", (False, None))
         if ddp[0]:
@@ -210,8 +253,10 @@ class MultimodalClassifier(B200Module):
             # same dropout masks to their shards (masks are a pure function of seed, site and element index)
             from .parallel import rank_seed
             seed = rank_seed(seed, ddp[1])
+        if explain is not None:
+            ddp = (False, None)
         logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes,
-                                  (self.num_classes, ddp[0], ddp[1]), *[p for _, p in named])
+                                  (self.num_classes, ddp[0], ddp[1], explain), *[p for _, p in named])
         if opts["train.bn_train"]:
             # the library wrote the new running_mean / running_var straight into the BatchNorm buffers
             # (momentum 0.1, unbiased variance: nn.BatchNorm2d in train mode); the step counters and the

@@ -1,0 +1,136 @@
+"""Grad-CAM on the drop-in model, with the reference notebook's own class (notebooks/explainability.ipynb cell 3).
+
+The notebook registers a forward hook and a full backward hook on `model.cnn_encoder.get_attention_layer()`
+(backbone.layer4, src/cnn_encoder.py:186-198), runs the model in eval mode WITH gradients enabled and calls
+`output['logits'][0, c].backward()`.  The drop-in serves that contract: a hooked layer4 switches the eval forward to
+the differentiable step (same kernels as the training forward, no dropout, BatchNorm on running statistics), the
+forward hook receives the layer4 map in the reference's NCHW fp32 layout and the backward hook d(logit)/d(map).
+
+Comparator: the oracle's restatement of the same computation under torch.autograd on the CPU (fp32).
+"""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from oracle import forward_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+class GradCAM:
+    """notebooks/explainability.ipynb cell 3, __init__ / hooks / generate_cam as written there."""
+
+    def __init__(self, model, target_layer):
+        self.model = model
+        self.target_layer = target_layer
+        self.gradients = None
+        self.activations = None
+
+        # Register hooks
+        self.target_layer.register_forward_hook(self._save_activation)
+        self.target_layer.register_full_backward_hook(self._save_gradient)
+
+    def _save_activation(self, module, input, output):
+        self.activations = output.detach()
+
+    def _save_gradient(self, module, grad_input, grad_output):
+        self.gradients = grad_output[0].detach()
+
+    def generate_cam(self, input_image, input_ids, attention_mask, target_class=None):
+        self.model.eval()
+
+        # Forward pass
+        output = self.model(input_image, input_ids, attention_mask)
+
+        if target_class is None:
+            target_class = output['logits'].argmax(dim=1).item()
+
+        # Backward pass
+        self.model.zero_grad()
+        output['logits'][0, target_class].backward()
+
+        # Generate CAM
+        gradients = self.gradients[0]  # [C, H, W]
+        activations = self.activations[0]  # [C, H, W]
+
+        # Global average pooling of gradients
+        weights = gradients.mean(dim=(1, 2), keepdim=True)
+
+        # Weighted sum of activations
+        cam = (weights * activations).sum(dim=0)
+        cam = F.relu(cam)  # Apply ReLU
+
+        # Normalize
+        cam = cam - cam.min()
+        cam = cam / (cam.max() + 1e-8)
+
+        return cam.cpu().numpy(), target_class, output['probs'][0, target_class].item()
+
+
+def _oracle_cam(sd, images, ids, mask, target_class):
+    """The same quantities from the oracle under autograd: layer4 map, d(logit)/d(map), logits."""
+    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    with torch.no_grad():
+        fmap = oracle.resnet50_feature_map(sd, images)
+        txt = oracle.text_encoder(sd, ids, mask)
+    fmap = fmap.clone().requires_grad_(True)
+    pooled = fmap.mean(dim=(2, 3))
+    h = F.relu(F.linear(pooled, sd["cnn_encoder.projection.0.weight"], sd["cnn_encoder.projection.0.bias"]))
+    img = F.linear(h, sd["cnn_encoder.projection.3.weight"], sd["cnn_encoder.projection.3.bias"])
+    fused, _ = oracle.attention_fusion(sd, img, txt)
+    logits = oracle.classification_head(sd, fused)
+    logits[0, target_class].backward()
+    return fmap.detach(), fmap.grad.detach(), logits.detach()
+
+
+def test_gradcam_with_the_notebook_class(cuda):
+    model = synth.build_model(0)
+    sd = synth.sensitise(model.state_dict(), 1)
+    model.load_state_dict(sd)
+    model = model.to(cuda)
+    images, ids, mask = synth.make_inputs(1, 128, 91, [77])
+    cam_tool = GradCAM(model, model.cnn_encoder.get_attention_layer())
+    cam, cls, conf = cam_tool.generate_cam(images.to(cuda), ids.to(cuda), mask.to(cuda))
+    assert cam.shape == (7, 7) and 0.0 <= cam.min() and cam.max() <= 1.0 + 1e-6
+    assert cam_tool.activations.shape == (1, 2048, 7, 7) and cam_tool.gradients.shape == (1, 2048, 7, 7)
+    fmap, dmap, logits = _oracle_cam(sd, images, ids, mask, cls)
+    assert int(logits.argmax(-1)) == cls and 0.0 < conf <= 1.0
+    act = cam_tool.activations.float().cpu()
+    grad = cam_tool.gradients.float().cpu()
+    rel_a = ((act - fmap).norm() / fmap.norm()).item()
+    rel_g = ((grad - dmap).norm() / dmap.norm()).item()
+    w_ref = dmap[0].mean(dim=(1, 2), keepdim=True)
+    cam_ref = F.relu((w_ref * fmap[0]).sum(0))
+    cam_ref = cam_ref - cam_ref.min()
+    cam_ref = cam_ref / (cam_ref.max() + 1e-8)
+    d_cam = (torch.from_numpy(cam) - cam_ref).abs().max().item()
+    print(f"Grad-CAM vs oracle autograd: layer4 map rel-L2 {rel_a:.4f}, gradient rel-L2 {rel_g:.4f}, "
+          f"max |cam - cam_ref| {d_cam:.4f} (cam in [0,1])")
+    assert rel_a <= 2e-2 and rel_g <= 5e-2 and d_cam <= 5e-2
+    # trainable parameters received gradients as they do under the reference's autograd; frozen ones none
+    assert model.classifier.classifier[0].weight.grad is not None
+    assert model.cnn_encoder.backbone.conv1.weight.grad is None
+
+
+def test_hooks_removed_restores_the_plain_eval_path(cuda):
+    """Without hooks the eval forward is the benchmarked inference path: no autograd graph, identical logits
+    whether or not gradients are enabled."""
+    model = synth.build_model(0).to(cuda)
+    images, ids, mask = synth.make_inputs(2, 32, 92, [32, 11])
+    images, ids, mask = images.to(cuda), ids.to(cuda), mask.to(cuda)
+    with torch.no_grad():
+        ref = model(images, ids, mask)["logits"]
+    layer = model.cnn_encoder.get_attention_layer()
+    seen = []
+    h = layer.register_forward_hook(lambda m, i, o: seen.append(tuple(o.shape)))
+    out = model(images, ids, mask)["logits"]
+    assert out.requires_grad and seen == [(2, 2048, 7, 7)]
+    assert (out.detach() - ref).abs().max().item() <= 2e-2   # fp32 batch-level layers vs bf16 ones
+    with torch.no_grad():                                     # forward hooks fire without autograd as well
+        out_ng = model(images, ids, mask)["logits"]
+    assert not out_ng.requires_grad and torch.equal(out_ng, out.detach()) and len(seen) == 2
+    h.remove()
+    out2 = model(images, ids, mask)["logits"]
+    assert not out2.requires_grad and torch.equal(out2, ref)

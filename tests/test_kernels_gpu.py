@@ -166,6 +166,33 @@ def test_conv3x3_flat(lib, cuda, N, H, W, Cin, Cout, act):
     _close(y.permute(0, 3, 1, 2), ref, what=f"flat 3x3 conv {Cin}->{Cout} {H}x{W}")
 
 
+@pytest.mark.parametrize("N,Ho,Wo,C0,C1,Cout,stride", [
+    (3, 56, 56, 64, 64, 256, 1),      # layer1.0: flat tiles, equal K halves
+    (2, 28, 28, 128, 256, 512, 2),    # layer2.0: block input read at stride 2, unequal K parts
+    (5, 14, 14, 256, 512, 1024, 2),   # layer3.0: two ragged tiles per image
+    (3, 7, 7, 512, 1024, 2048, 2),    # layer4.0: two images per tile, odd batch
+    (1, 10, 6, 64, 128, 64, 2),       # narrow output (N = 64 tile), non-square
+])
+def test_conv1x1_dual(lib, cuda, N, Ho, Wo, C0, C1, Cout, stride):
+    """conv3 + downsample + add + ReLU as one K-concatenated GEMM == the two convolutions summed."""
+    g = torch.Generator(device="cuda").manual_seed(Ho * Wo + C1)
+    x0 = torch.randn(N, C0, Ho, Wo, device=cuda, generator=g).to(BF)
+    x1 = torch.randn(N, C1, Ho * stride, Wo * stride, device=cuda, generator=g).to(BF)
+    w0 = (torch.randn(Cout, C0, 1, 1, device=cuda, generator=g) / math.sqrt(C0)).to(BF)
+    w1 = (torch.randn(Cout, C1, 1, 1, device=cuda, generator=g) / math.sqrt(C1)).to(BF)
+    bias = torch.randn(Cout, device=cuda, generator=g)
+    wcat = torch.cat([w0.view(Cout, C0), w1.view(Cout, C1)], dim=1).contiguous()
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=cuda, dtype=BF)
+    x0_nhwc = x0.permute(0, 2, 3, 1).contiguous()   # named: both operands must stay alive across the call
+    x1_nhwc = x1.permute(0, 2, 3, 1).contiguous()
+    _check(lib, lib.mrd_conv1x1_dual_bf16(x0_nhwc.data_ptr(), C0, x1_nhwc.data_ptr(), C1, stride, N, Ho, Wo,
+                                          wcat.data_ptr(), Cout, bias.data_ptr(), y.data_ptr(), 1, _stream()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x0.float(), w0.float()) + F.conv2d(x1.float(), w1.float(), stride=stride)
+                 + bias.view(1, -1, 1, 1))
+    _close(y.permute(0, 3, 1, 2), ref, what=f"dual 1x1 conv {C0}+{C1}->{Cout} stride {stride}")
+
+
 def test_conv3x3_flat_rejects_unsupported(lib, cuda):
     # the resident 3x3 weight panel of Cin=128 does not fit next to two 56-wide halo spans
     x = torch.zeros(1, 58, 58, 128, device=cuda, dtype=BF)
@@ -267,7 +294,8 @@ def test_bert_embed(lib, cuda):
 # ------------------------------------------------------------------ attention (K3)
 @pytest.fixture(params=["tcgen05", "mma.sync"])
 def attn_path(request, lib):
-    """S <= 128 has two implementations: run the attention tests through both."""
+    """Two implementations: tcgen05 (one 128x128 tile for S <= 128, key-block loop with a running softmax up to
+    S = 512) and the mma.sync flash kernel (kept as the cross-check): run the attention tests through both."""
     lib.mrd_attention_use_tcgen05(1 if request.param == "tcgen05" else 0)
     yield request.param
     lib.mrd_attention_use_tcgen05(1)
@@ -279,6 +307,10 @@ def attn_path(request, lib):
     (2, 512, 12, [512, 65]),       # whole key blocks skipped
     (3, 48, 4, [48, 33, 5]),       # S < 64: BLOCK_M = 64 path, ragged
     (2, 200, 12, [200, 129]),      # S not a multiple of 64
+    (1, 256, 12, None),            # two full key blocks, no mask
+    (3, 320, 4, [320, 128, 129]),  # lengths on and just past a key-block boundary
+    (2, 384, 12, [384, 257]),      # three key blocks, last query block with one row
+    (40, 512, 12, None),           # more work items than resident CTAs (persistence, barrier phases)
 ])
 def test_attention(lib, cuda, attn_path, B, S, heads, lengths):
     g = torch.Generator(device="cuda").manual_seed(S + B)

@@ -73,6 +73,9 @@ def test_benchmark_scale_parity(cuda, batch, weights):
     margin = (top2[:, 0] - top2[:, 1])
     flips = (lg.argmax(-1) != rl.argmax(-1))
     rels = {k: _rel_rows(fast[k], ref[k]).max().item() for k in ("image_embedding", "text_embedding", "fused_embedding")}
+    lrel = _rel_rows(lg, rl)
+    print(f"\n[{weights}] per-row logits rel-L2: median {lrel.median().item():.4f}, p99 "
+          f"{lrel.quantile(0.99).item():.4f}, max {lrel.max().item():.4f}")
     print(f"\n[{weights}] {N} samples vs fp32 check: top-1 agreement {agree * 100:.3f} % ({int(flips.sum())} flips, "
           f"fp32 margins of the flipped rows: {[round(v, 4) for v in margin[flips].tolist()][:8]}), "
           f"logits max-abs err {err:.4g} (scale {scale:.3g}, bar {2e-2 * scale:.3g}), "

