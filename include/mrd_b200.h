@@ -244,15 +244,29 @@ int mrd_train_backward(mrd_ctx* ctx, const float* dlogits, int n, const char* co
 /* The same two calls with the extra tensors Grad-CAM needs (notebooks/explainability.ipynb cell 3 hooks
  * cnn_encoder.get_attention_layer() = backbone.layer4, src/cnn_encoder.py:186-198, and back-propagates one logit):
  * feat_map (optional): f32 [B,2048,H/32,W/32] NCHW, the layer4 output of this forward (BatchNorm on running
- * statistics only); d_pooled (optional): f32 [B,2048] = d(loss)/d(backbone output after global average pooling), from
+ * statistics only); img_emb / txt_emb / fused (optional): the three embeddings of this forward as
+ * MultimodalClassifier.forward(return_embeddings=True) returns them (src/multimodal_classifier.py:168-175), f32
+ * [B,512] / [B,768] / [B,512]; d_pooled (optional): f32 [B,2048] = d(loss)/d(backbone output after global average pooling), from
  * which d(loss)/d(layer4 output) = d_pooled / (H/32 * W/32) at every position.  With every dropout probability 0
  * this is the eval-mode forward made differentiable.  When no text_encoder.* gradient is requested the text branch
  * of the backward is skipped. */
 int mrd_train_forward_ex(mrd_ctx* ctx, const void* images, int img_dtype, const long long* ids,
                          const void* mask, int mask_dtype, int B, int H, int W, int S,
-                         unsigned long long seed, float* logits, float* feat_map, void* stream);
+                         unsigned long long seed, float* logits, float* feat_map, float* img_emb,
+                         float* txt_emb, float* fused, void* stream);
 int mrd_train_backward_ex(mrd_ctx* ctx, const float* dlogits, int n, const char* const* names,
                           float* const* grads, float* d_pooled, void* stream);
+
+/* The backward in stages, for data-parallel hosts that overlap the gradient all-reduce with the rest of the backward
+ * (SURVEY.md 8(e)): _begin takes what mrd_train_backward_ex takes and enqueues nothing; _stages runs stages
+ * [first, last) on `stream` - they must be run in order, each once.  Stage 0 = head + fusion + image projection (all
+ * their gradients are complete when it returns), stage 1 + k = BERT layer (layers - 1 - k), the last stage = the
+ * embeddings; mrd_train_backward_num_stages = layers + 2.  The gradient buffers handed to _begin must stay valid
+ * until the last stage has been enqueued. */
+int mrd_train_backward_begin(mrd_ctx* ctx, const float* dlogits, int n, const char* const* names,
+                             float* const* grads, float* d_pooled);
+int mrd_train_backward_stages(mrd_ctx* ctx, int first, int last, void* stream);
+int mrd_train_backward_num_stages(mrd_ctx* ctx);
 
 /* out[i] = 1 if element i of dropout site `site` is kept under (seed, p), else 0 (i < n).  The masks
  * of mrd_train_forward are reproducible with this (tests; csrc/rng.cuh documents the site ids and the

@@ -1476,21 +1476,23 @@ int mrd_ctx_profile_report(mrd_ctx* c, char* buf, int cap) {
 
 int mrd_train_forward_ex(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
                          int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
-                         float* feat_map, void* stream) {
+                         float* feat_map, float* img_emb, float* txt_emb, float* fused, void* stream) {
     MRD_TRY(check_ctx(c));
     if (B <= 0) return 0;
     if (mask && (mask_dtype < MRD_DT_I64 || mask_dtype > MRD_DT_BF16)) {
         set_last_error("unknown mask dtype code %d", mask_dtype);
         return -1;
     }
-    return train_forward(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, feat_map,
-                         static_cast<cudaStream_t>(stream));
+    MRD_TRY(train_forward(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, feat_map,
+                          static_cast<cudaStream_t>(stream)));
+    return train_export_embeddings(c, B, img_emb, txt_emb, fused, static_cast<cudaStream_t>(stream));
 }
 
 int mrd_train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long* ids, const void* mask,
                       int mask_dtype, int B, int H, int W, int S, unsigned long long seed, float* logits,
                       void* stream) {
-    return mrd_train_forward_ex(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, nullptr, stream);
+    return mrd_train_forward_ex(c, images, img_dtype, ids, mask, mask_dtype, B, H, W, S, seed, logits, nullptr, nullptr,
+                                nullptr, nullptr, stream);
 }
 
 int mrd_train_backward_ex(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,
@@ -1501,6 +1503,26 @@ int mrd_train_backward_ex(mrd_ctx* c, const float* dlogits, int n, const char* c
     for (int i = 0; i < n; ++i)
         if (grads[i]) gt.emplace(names[i], grads[i]);
     return train_backward(c, dlogits, gt, d_pooled, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_train_backward_begin(mrd_ctx* c, const float* dlogits, int n, const char* const* names,
+                             float* const* grads, float* d_pooled) {
+    MRD_TRY(check_ctx(c));
+    GradTable gt;
+    gt.reserve(static_cast<size_t>(n) * 2);
+    for (int i = 0; i < n; ++i)
+        if (grads[i]) gt.emplace(names[i], grads[i]);
+    return train_backward_begin(c, dlogits, gt, d_pooled);
+}
+
+int mrd_train_backward_stages(mrd_ctx* c, int first, int last, void* stream) {
+    MRD_TRY(check_ctx(c));
+    return train_backward_run(c, first, last, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_train_backward_num_stages(mrd_ctx* c) {
+    if (!c) return -1;
+    return train_backward_stages(c);
 }
 
 int mrd_train_backward(mrd_ctx* c, const float* dlogits, int n, const char* const* names, float* const* grads,

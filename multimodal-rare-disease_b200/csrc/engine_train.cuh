@@ -70,6 +70,12 @@ struct TrainState {
           *pre_i = nullptr, *pre_t = nullptr, *cat = nullptr, *fh = nullptr, *fused = nullptr;
     std::vector<float*> hh;               // head hidden activations (post dropout)
     float *g0 = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr, *g4 = nullptr;  // [B, 2048] gradient scratch
+    // staged backward (train_backward_begin / train_backward_run)
+    bool bw_active = false, bw_want_text = false;
+    int bw_next = 0;
+    const float* bw_dlogits = nullptr;
+    float* bw_d_pooled = nullptr;
+    std::unordered_map<std::string, float*> bw_grads;
     // forward bookkeeping
     bool fwd_done = false;
     unsigned long long seed = 0;
@@ -692,6 +698,20 @@ int train_forward(mrd_ctx* c, const void* images, int img_dtype, const long long
     return 0;
 }
 
+// image / text / fused embeddings of the pending forward (fp32 activations of the batch-level layers)
+int train_export_embeddings(mrd_ctx* c, int B, float* img_emb, float* txt_emb, float* fused, cudaStream_t s) {
+    TrainState* t = train_state(c);
+    const struct { float* dst; const float* src; int w; } out[3] = {
+        {img_emb, t->img, c->proj2.out}, {txt_emb, t->txt, c->hidden}, {fused, t->fused, c->fusion_dim}};
+    for (const auto& o : out) {
+        if (!o.dst) continue;
+        cudaError_t e = cudaMemcpyAsync(o.dst, o.src, sizeof(float) * static_cast<size_t>(B) * o.w,
+                                        cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(embedding export)");
+    }
+    return 0;
+}
+
 // dW = dY^T X through the tcgen05 GEMM: stage both operands token-minor (the bias gradient = column sums of dY
 // is taken by the same staging kernel), fp32 result into `dst`.  Either destination may be null.
 int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* dY, int n_out, const bf16* X, int n_in,
@@ -705,8 +725,16 @@ int train_wgrad(mrd_ctx* c, TrainState* t, const GemmLaunch& plan, const bf16* d
     return run_f32(c, "train.wgrad", plan, dst, n_in, s);
 }
 
-int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float* d_pooled, cudaStream_t s) {
+// The backward is cut into stages so that a data-parallel host can start the all-reduce of a gradient bucket as
+// soon as the stage that completes it has been enqueued (bucketed, overlapped with backward):
+//   stage 0                head, fusion, image projection, TextEncoder.dropout, CLS scatter
+//   stage 1 + k            BERT layer (layers-1-k), k = 0 .. layers-1  (reverse order)
+//   stage layers + 1       embeddings
+int train_backward_stages(mrd_ctx* c) { return static_cast<int>(c->layers.size()) + 2; }
+
+int train_backward_begin(mrd_ctx* c, const float* dlogits, const GradTable& gt, float* d_pooled) {
     TrainState* t = train_state(c);
+    t->bw_active = false;
     if (!t->fwd_done) {
         set_last_error("mrd_train_backward: no forward is pending on this context");
         return -1;
@@ -717,12 +745,40 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float*
                        "token-packing tables it saved were overwritten)");
         return -1;
     }
+    t->bw_dlogits = dlogits;
+    t->bw_grads = gt;
+    t->bw_d_pooled = d_pooled;
+    t->bw_want_text = false;
+    for (const auto& kv : gt) t->bw_want_text |= kv.first.rfind("text_encoder.", 0) == 0;
+    t->bw_next = 0;
+    t->bw_active = true;
+    return 0;
+}
+
+// runs stages [lo, hi) of the pending backward; stages must be run in order, each exactly once
+int train_backward_run(mrd_ctx* c, int lo, int hi, cudaStream_t s) {
+    TrainState* t = train_state(c);
+    const int n_stages = train_backward_stages(c);
+    if (!t->bw_active || lo != t->bw_next || hi <= lo || hi > n_stages) {
+        set_last_error("mrd_train_backward_stage: stages [%d, %d) out of order (next %d of %d, %s)", lo, hi,
+                       t->bw_next, n_stages, t->bw_active ? "active" : "no backward begun");
+        return -1;
+    }
+    t->bw_next = hi;
+    if (hi == n_stages) t->bw_active = false;
+    auto runs = [&](int st) { return lo <= st && st < hi; };
+    const GradTable& gt = t->bw_grads;
+    const float* dlogits = t->bw_dlogits;
+    float* d_pooled = t->bw_d_pooled;
     const TrainOpts& o = t->o;
     const unsigned long long seed = t->seed;
     const int B = t->B, S = t->S, T = t->Ta, Hd = c->hidden, F = c->ffn, Fd = c->fusion_dim;
     const int hd = Fd / c->fusion_heads;
     const long long nB = B;
 
+    const size_t nl = c->layers.size();
+    bf16* dx_top = (nl & 1) ? t->dxb : t->dxa;   // layer nl-1 reads dx[nl & 1]
+    if (runs(0)) {
     // ---- head
     const size_t nh = c->head_hidden.size();
     const float* dy = dlogits;
@@ -792,9 +848,7 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float*
     // d_pooled (optional): gradient of the backbone's pooled output - what Grad-CAM spreads over the layer4 map
     MRD_TRY(lin_bwd(c, gt, "cnn_encoder.projection.0", t->pooled, c->feat_dim, t->g0, c->proj1.out, B, d_pooled,
                     c->feat_dim, nullptr, 0, s));
-    bool want_text = false;
-    for (const auto& kv : gt) want_text |= kv.first.rfind("text_encoder.", 0) == 0;
-    if (!want_text) return 0;   // nothing below the text embedding is differentiated (Grad-CAM with a frozen encoder)
+    if (!t->bw_want_text) return 0;   // nothing below the text embedding is differentiated (frozen text encoder)
 
     // ---- text branch: TextEncoder.dropout, CLS scatter, then the encoder layers in reverse
     TRK("train.dropout", CAT_MEM, dropout_f32(d_txt, B, Hd, make_drop(seed, SITE_TEXT_OUT, o.p_text_out), d_txt, s));
@@ -802,13 +856,14 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float*
         ++c->launches;
         return fp32_bert_train_backward(c->raw, c->f32_opts(), &c->f32_train, d_txt, gt, o.pad_idx, s);
     }
-    const size_t nl = c->layers.size();
-    bf16* dx_top = (nl & 1) ? t->dxb : t->dxa;   // layer nl-1 reads dx[nl & 1]
     cudaError_t e = cudaMemsetAsync(dx_top, 0, sizeof(bf16) * static_cast<size_t>(T) * Hd, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dX)");
     TRK("train.cls", CAT_MEM, scatter_cls_rows_bf16(d_txt, c->t_seq_off, B, Hd, dx_top, s));
+    }   // stage 0
+    if (!t->bw_want_text || c->fp32_check) return 0;   // stage 0 did everything there is to do
     const std::string enc = "text_encoder.encoder.encoder.layer.";
     for (size_t i = nl; i-- > 0;) {
+        if (!runs(1 + static_cast<int>(nl - 1 - i))) continue;
         const BertLayerW& Lw = c->layers[i];
         const TrainLayerBuf& b = t->L[i];
         TrainLayerPlan& p = t->P[i];
@@ -878,6 +933,7 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float*
         }
         MRD_TRY(run(c, "train.dgrad", p.d_x, s));    // dx_i = dqkv Wqkv + d_s1
     }
+    if (!runs(static_cast<int>(nl) + 1)) return 0;
     // ---- embeddings: dropout, LayerNorm backward, scatter-add into the three tables
     bf16* dx0 = t->dxa;   // layer 0 wrote dx[0]
     TRK("train.dropout", CAT_MEM, dropout_bf16(dx0, Hd, T, Hd, c->t_nrows, make_drop(seed, SITE_EMB, o.p_bert_hidden), dx0, Hd, s));
@@ -890,7 +946,12 @@ int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float*
     if (g_word || g_pos || g_type || g_lg || g_lb)
         TRK("train.embed_bwd", CAT_MEM, embed_ln_bwd(t->ids, c->t_row_tok, T, c->t_nrows, S, c->word_emb, c->pos_type, c->emb_g,
                              c->bert_ln_eps, c->vocab, o.pad_idx, dx0, g_word, g_pos, g_type, g_lg, g_lb, s));
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "training backward");
     return 0;
+}
+
+int train_backward(mrd_ctx* c, const float* dlogits, const GradTable& gt, float* d_pooled, cudaStream_t s) {
+    MRD_TRY(train_backward_begin(c, dlogits, gt, d_pooled));
+    return train_backward_run(c, 0, train_backward_stages(c), s);
 }

@@ -212,6 +212,8 @@ class Engine:
         emb = self._f32(B, emb_dim)
         pooled = self._f32(B, 2048) if want_pooled else None
         fmap = self._f32(B, 2048, H // 32, W // 32) if want_map else None
+        embs = [self._f32(B, d) for d in emb_dims] if emb_dims else [None, None, None]
+        self.last_train_embeddings = embs if emb_dims else None
         if B:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.mrd_cnn_encoder_fwd(self._ctx, images.data_ptr(), code, B, H, W,
@@ -298,9 +300,11 @@ class Engine:
 
     # ------------------------------------------------------------------ training step
     def train_forward(self, images, input_ids, attention_mask, num_classes: int, seed: int,
-                      want_map: bool = False):
+                      want_map: bool = False, emb_dims=None):
         """Train-mode forward (dropout active, activations kept inside the context) -> logits f32 [B,C]
-        (and, with want_map, the layer4 feature map f32 [B,2048,H/32,W/32] of this forward)."""
+        (and, with want_map, the layer4 feature map f32 [B,2048,H/32,W/32] of this forward).
+        emb_dims = (image, text, fused) widths: the three embeddings of this forward are kept in
+        self.last_train_embeddings (what return_embeddings=True hands out)."""
         images, icode = self._images(images)
         ids, mask, mcode = self._text(input_ids, attention_mask)
         B, _, H, W = images.shape
@@ -308,6 +312,8 @@ class Engine:
             raise ValueError(f"batch mismatch: {B} images vs {ids.shape[0]} token rows")
         logits = self._f32(B, num_classes)
         fmap = self._f32(B, 2048, H // 32, W // 32) if want_map else None
+        embs = [self._f32(B, d) for d in emb_dims] if emb_dims else [None, None, None]
+        self.last_train_embeddings = embs if emb_dims else None
         self._train_inputs = (images, ids, mask)   # the backward re-reads the ids
         self.train_serial = getattr(self, "train_serial", 0) + 1
         if B:
@@ -315,19 +321,38 @@ class Engine:
                 _lib.check(self.lib.mrd_train_forward_ex(
                     self._ctx, images.data_ptr(), icode, ids.data_ptr(), _ptr(mask), mcode, B, H, W,
                     ids.shape[1], C.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), logits.data_ptr(), _ptr(fmap),
-                    _stream(self.device)), "mrd_train_forward")
+                    _ptr(embs[0]), _ptr(embs[1]), _ptr(embs[2]), _stream(self.device)), "mrd_train_forward")
         return (logits, fmap) if want_map else logits
 
-    def train_backward(self, dlogits: torch.Tensor, named_shapes, want_dpooled: bool = False):
+    def _backward_stage_of(self, name: str, n_layers: int) -> int:
+        """Stage of mrd_train_backward_stages that completes the gradient of parameter `name`."""
+        pre = "text_encoder.encoder.encoder.layer."
+        if name.startswith(pre):
+            return 1 + (n_layers - 1 - int(name[len(pre):].split(".", 1)[0]))
+        if name.startswith("text_encoder."):
+            return n_layers + 1          # embeddings
+        return 0                         # head, fusion, image projection
+
+    def train_backward(self, dlogits: torch.Tensor, named_shapes, want_dpooled: bool = False, on_bucket=None):
         """named_shapes: [(canonical state_dict name, shape)] of the parameters that want a gradient.
-        Returns their f32 gradients as views of ONE flat buffer (a single all-reduce bucket); with want_dpooled
-        also d(loss)/d(pooled backbone features) f32 [B,2048]."""
+        Returns their f32 gradients as views of ONE flat buffer, laid out in the order the backward completes
+        them (head / fusion / projection, BERT layers last to first, embeddings); with want_dpooled also
+        d(loss)/d(pooled backbone features) f32 [B,2048].
+        on_bucket(flat_slice): data-parallel overlap - the backward is enqueued stage by stage and the callback
+        receives each finished slice of the flat buffer right after its stage (it typically starts an
+        asynchronous all-reduce that then runs under the remaining stages)."""
         dl = dlogits.to(self.device, torch.float32).contiguous()
+        n_stages = int(self.lib.mrd_train_backward_num_stages(self._ctx))
+        stage = [self._backward_stage_of(name, n_stages - 2) for name, _ in named_shapes]
+        order = sorted(range(len(named_shapes)), key=lambda i: stage[i])   # stable: module order inside a stage
         sizes = [int(torch.Size(sh).numel()) for _, sh in named_shapes]
-        offs, tot = [], 0
-        for n in sizes:
-            offs.append(tot)
-            tot += (n + 3) // 4 * 4      # keep every view 16-byte aligned
+        offs, tot, bounds = [0] * len(named_shapes), 0, [0] * (n_stages + 1)
+        for i in order:
+            offs[i] = tot
+            tot += (sizes[i] + 3) // 4 * 4      # keep every view 16-byte aligned
+            bounds[stage[i] + 1] = tot
+        for st in range(1, n_stages + 1):
+            bounds[st] = max(bounds[st], bounds[st - 1])
         flat = torch.zeros(max(tot, 4), dtype=torch.float32, device=self.device)
         n = len(named_shapes)
         names = (C.c_char_p * n)()
@@ -341,8 +366,18 @@ class Engine:
         d_pooled = torch.zeros(dl.shape[0], 2048, dtype=torch.float32, device=self.device) if want_dpooled else None
         if dl.shape[0]:
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.mrd_train_backward_ex(self._ctx, dl.data_ptr(), n, names, ptrs, _ptr(d_pooled),
-                                                          _stream(self.device)), "mrd_train_backward")
+                if on_bucket is None:
+                    _lib.check(self.lib.mrd_train_backward_ex(self._ctx, dl.data_ptr(), n, names, ptrs,
+                                                              _ptr(d_pooled), _stream(self.device)),
+                               "mrd_train_backward")
+                else:
+                    _lib.check(self.lib.mrd_train_backward_begin(self._ctx, dl.data_ptr(), n, names, ptrs,
+                                                                 _ptr(d_pooled)), "mrd_train_backward_begin")
+                    for st in range(n_stages):
+                        _lib.check(self.lib.mrd_train_backward_stages(self._ctx, st, st + 1, _stream(self.device)),
+                                   "mrd_train_backward_stages")
+                        if bounds[st + 1] > bounds[st]:
+                            on_bucket(flat[bounds[st]:bounds[st + 1]])
         self._train_inputs = None
         self.last_flat_grad = flat
         return (views, d_pooled) if want_dpooled else views

@@ -36,10 +36,12 @@ class _TrainStep(torch.autograd.Function):
         forward / backward hooks are served (Grad-CAM on cnn_encoder.get_attention_layer()) or None."""
         ctx.eng, ctx.named_shapes, ctx.ddp = eng, named_shapes, ddp
         ctx.hooked = ddp[3] if len(ddp) > 3 else None
+        emb_dims = ddp[4] if len(ddp) > 4 else None
         if ctx.hooked is None:
-            logits = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed)
+            logits = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed, emb_dims=emb_dims)
         else:
-            logits, fmap = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed, want_map=True)
+            logits, fmap = eng.train_forward(images, input_ids, attention_mask, ddp[0], seed, want_map=True,
+                                             emb_dims=emb_dims)
             ctx.map_shape = tuple(fmap.shape)
             # forward hooks of the hooked module see its output as the reference's would (NCHW fp32); the module's
             # input (layer3's output) is not materialised in that layout: hooks get an empty input tuple
@@ -63,12 +65,18 @@ class _TrainStep(torch.autograd.Function):
             d_map = (d_pooled / float(h * w)).view(Bn, Cn, 1, 1).expand(Bn, Cn, h, w).contiguous()
             for hook in list(ctx.hooked._backward_hooks.values()):
                 hook(ctx.hooked, (None,), (d_map,))
+        elif ctx.ddp[1]:
+            # data parallel: the gradients live in one flat buffer laid out in completion order; the averaging
+            # all-reduce of each bucket (one per backward stage: head + fusion + projection, every BERT layer, the
+            # embeddings) is started as soon as its stage is enqueued and runs under the remaining stages
+            from .parallel import allreduce_mean_async, wait_allreduce
+            pending = []
+            grads = ctx.eng.train_backward(dlogits, ctx.named_shapes,
+                                           on_bucket=lambda b: pending.append(allreduce_mean_async(b, ctx.ddp[2])))
+            for h in pending:
+                wait_allreduce(h)
         else:
             grads = ctx.eng.train_backward(dlogits, ctx.named_shapes)
-        if ctx.ddp[1]:
-            # data parallel: every gradient of the step lives in one flat buffer -> one all-reduce
-            from .parallel import allreduce_mean_
-            allreduce_mean_(ctx.eng.last_flat_grad, ctx.ddp[2])
         return (None,) * 7 + tuple(grads)
 
 
@@ -157,12 +165,11 @@ class MultimodalClassifier(B200Module):
         self.text_encoder._check()
         if self.training:
             return self._forward_train(images, input_ids, attention_mask, return_embeddings)
-        if not return_embeddings:
-            hooked = self._hooked_attention_layer()
-            if hooked is not None:
-                # Grad-CAM (notebooks/explainability.ipynb cell 3): hooks on cnn_encoder.get_attention_layer() and
-                # logits[0, c].backward() under model.eval() - the eval-mode forward made differentiable
-                return self._forward_train(images, input_ids, attention_mask, False, explain=hooked)
+        hooked = self._hooked_attention_layer()
+        if hooked is not None:
+            # Grad-CAM (notebooks/explainability.ipynb cell 3): hooks on cnn_encoder.get_attention_layer() and
+            # logits[0, c].backward() under model.eval() - the eval-mode forward made differentiable
+            return self._forward_train(images, input_ids, attention_mask, return_embeddings, explain=hooked)
         logits, probs, img_e, txt_e, fused, a1, a2 = self._engine().multimodal(
             images, input_ids, attention_mask, self._dims(), want_embeddings=return_embeddings,
             logits_out=logits_out)
@@ -220,8 +227,6 @@ class MultimodalClassifier(B200Module):
         training loops (src/train.py:247-333, src/train_multimodal.py:508-556) run unchanged.
         explain = a hooked backbone module: the same machinery in EVAL semantics (no dropout, BatchNorm on running
         statistics) with the module's hooks served - what Grad-CAM needs."""
-        if return_embeddings:
-            raise NotImplementedError("return_embeddings=True is an inference-path feature (eval mode)")
         p_att = {self.fusion.fusion_layer.image_to_text_attention.dropout.p,
                  self.fusion.fusion_layer.text_to_image_attention.dropout.p,
                  self.fusion.fusion_layer.fusion[2].p}
@@ -255,8 +260,10 @@ class MultimodalClassifier(B200Module):
             seed = rank_seed(seed, ddp[1])
         if explain is not None:
             ddp = (False, None)
+        emb_dims = ((self.cnn_encoder.embedding_dim, self.text_encoder.embedding_dim, self.fusion_dim)
+                    if return_embeddings else None)
         logits = _TrainStep.apply(eng, images, input_ids, attention_mask, seed, shapes,
-                                  (self.num_classes, ddp[0], ddp[1], explain), *[p for _, p in named])
+                                  (self.num_classes, ddp[0], ddp[1], explain, emb_dims), *[p for _, p in named])
         if opts["train.bn_train"]:
             # the library wrote the new running_mean / running_var straight into the BatchNorm buffers
             # (momentum 0.1, unbiased variance: nn.BatchNorm2d in train mode); the step counters and the
@@ -274,13 +281,22 @@ class MultimodalClassifier(B200Module):
                 broadcast_buffers_([b for m in self.cnn_encoder.backbone.modules()
                                     if isinstance(m, nn.modules.batchnorm._BatchNorm)
                                     for b in (m.running_mean, m.running_var) if b is not None], ddp[1])
-        return {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
+        out = {"logits": logits, "probs": torch.softmax(logits, dim=-1)}
+        if return_embeddings:
+            # values of this forward (src/multimodal_classifier.py:168-175); gradients flow through the logits only
+            img_e, txt_e, fused = eng.last_train_embeddings
+            heads = self.config.fusion.num_attention_heads
+            ones = torch.ones(logits.shape[0], heads, 1, 1, dtype=torch.float32, device=logits.device)
+            out.update({"image_embedding": img_e, "text_embedding": txt_e, "fused_embedding": fused,
+                        "attention_info": {"image_to_text_attention": ones, "text_to_image_attention": ones.clone()}})
+        return out
 
     def data_parallel(self, enabled: bool = True, process_group=None) -> "MultimodalClassifier":
         """Training on several GPUs (one process per GPU, replicated parameters, each rank its own
-        batch shard): average the parameter gradients over the ranks inside loss.backward() - a single
-        all-reduce of the step's flat gradient buffer over NCCL.  The caller keeps the ranks' parameters
-        identical at the start (same seed or a broadcast), exactly as with DistributedDataParallel."""
+        batch shard): average the parameter gradients over the ranks inside loss.backward() - bucketed
+        all-reduces over NCCL (one bucket per backward stage), each started while the remaining stages are
+        still running.  The caller keeps the ranks' parameters identical at the start (same seed or a
+        broadcast), exactly as with DistributedDataParallel."""
         self.__dict__["_mrd_ddp"] = (bool(enabled), process_group)
         return self
 

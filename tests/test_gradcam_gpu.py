@@ -69,12 +69,15 @@ class GradCAM:
         return cam.cpu().numpy(), target_class, output['probs'][0, target_class].item()
 
 
-def _oracle_cam(sd, images, ids, mask, target_class):
-    """The same quantities from the oracle under autograd: layer4 map, d(logit)/d(map), logits."""
+def _oracle_cam(sd, images, ids, mask, target_class, fmap=None, txt=None):
+    """The same quantities from the oracle under autograd: layer4 map, d(logit)/d(map), logits.  fmap / txt given:
+    the differentiated tail (avgpool -> projection -> fusion -> head, all fp32) is evaluated at THOSE activations."""
     sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
     with torch.no_grad():
-        fmap = oracle.resnet50_feature_map(sd, images)
-        txt = oracle.text_encoder(sd, ids, mask)
+        if fmap is None:
+            fmap = oracle.resnet50_feature_map(sd, images)
+        if txt is None:
+            txt = oracle.text_encoder(sd, ids, mask)
     fmap = fmap.clone().requires_grad_(True)
     pooled = fmap.mean(dim=(2, 3))
     h = F.relu(F.linear(pooled, sd["cnn_encoder.projection.0.weight"], sd["cnn_encoder.projection.0.bias"]))
@@ -85,30 +88,53 @@ def _oracle_cam(sd, images, ids, mask, target_class):
     return fmap.detach(), fmap.grad.detach(), logits.detach()
 
 
-def test_gradcam_with_the_notebook_class(cuda):
+def _cam(fmap, dmap):
+    w = dmap[0].mean(dim=(1, 2), keepdim=True)
+    cam = F.relu((w * fmap[0]).sum(0))
+    cam = cam - cam.min()
+    return cam / (cam.max() + 1e-8)
+
+
+@pytest.mark.parametrize("weights", ["plain", "sens"])
+def test_gradcam_with_the_notebook_class(cuda, weights):
     model = synth.build_model(0)
-    sd = synth.sensitise(model.state_dict(), 1)
-    model.load_state_dict(sd)
+    sd = model.state_dict()
+    if weights == "sens":
+        sd = synth.sensitise(sd, 1)
+        model.load_state_dict(sd)
     model = model.to(cuda)
     images, ids, mask = synth.make_inputs(1, 128, 91, [77])
     cam_tool = GradCAM(model, model.cnn_encoder.get_attention_layer())
     cam, cls, conf = cam_tool.generate_cam(images.to(cuda), ids.to(cuda), mask.to(cuda))
+    with torch.no_grad():   # the text embedding of this very path (hooks registered -> the differentiable forward)
+        emb = model(images.to(cuda), ids.to(cuda), mask.to(cuda), return_embeddings=True)
+    txt_ours = emb["text_embedding"].float().cpu()
+    assert emb["image_embedding"].shape == (1, 512) and emb["fused_embedding"].shape == (1, 512)
     assert cam.shape == (7, 7) and 0.0 <= cam.min() and cam.max() <= 1.0 + 1e-6
     assert cam_tool.activations.shape == (1, 2048, 7, 7) and cam_tool.gradients.shape == (1, 2048, 7, 7)
-    fmap, dmap, logits = _oracle_cam(sd, images, ids, mask, cls)
-    assert int(logits.argmax(-1)) == cls and 0.0 < conf <= 1.0
     act = cam_tool.activations.float().cpu()
     grad = cam_tool.gradients.float().cpu()
+    # (1) the hooked activation is the reference's layer4 output
+    fmap, dmap, logits = _oracle_cam(sd, images, ids, mask, cls)
+    assert int(logits.argmax(-1)) == cls and 0.0 < conf <= 1.0
     rel_a = ((act - fmap).norm() / fmap.norm()).item()
+    # (2) the hooked gradient is autograd's through the fp32 tail evaluated at the SAME activations (the layer4
+    # map the hook saw, the text embedding of this path): isolates the backward from forward rounding
+    _, dmap_same, _ = _oracle_cam(sd, images, ids, mask, cls, fmap=act, txt=txt_ours)
+    rel_g_same = ((grad - dmap_same).norm() / dmap_same.norm()).item()
+    # (3) end to end against the pure fp32 oracle: bf16 forward rounding flips a few ReLU gates of the projection /
+    # fusion MLP / head, which moves d(logit)/d(map) by percents (most with the sensitised x2..x4 weights)
     rel_g = ((grad - dmap).norm() / dmap.norm()).item()
-    w_ref = dmap[0].mean(dim=(1, 2), keepdim=True)
-    cam_ref = F.relu((w_ref * fmap[0]).sum(0))
-    cam_ref = cam_ref - cam_ref.min()
-    cam_ref = cam_ref / (cam_ref.max() + 1e-8)
+    cam_ref = _cam(fmap, dmap)
     d_cam = (torch.from_numpy(cam) - cam_ref).abs().max().item()
-    print(f"Grad-CAM vs oracle autograd: layer4 map rel-L2 {rel_a:.4f}, gradient rel-L2 {rel_g:.4f}, "
-          f"max |cam - cam_ref| {d_cam:.4f} (cam in [0,1])")
-    assert rel_a <= 2e-2 and rel_g <= 5e-2 and d_cam <= 5e-2
+    corr = torch.corrcoef(torch.stack([torch.from_numpy(cam).flatten(), cam_ref.flatten()]))[0, 1].item()
+    print(f"[{weights}] Grad-CAM: layer4 map rel-L2 {rel_a:.4f}; gradient vs autograd at the same activations "
+          f"{rel_g_same:.2e}; end to end vs the fp32 oracle: gradient rel-L2 {rel_g:.4f}, max |cam - cam_ref| "
+          f"{d_cam:.4f}, cam correlation {corr:.4f}")
+    assert rel_a <= 2e-2
+    assert rel_g_same <= 5e-3
+    assert rel_g <= 2e-1      # measured 0.11 (plain) / 0.12 (sens): ReLU-gate flips, see (3)
+    assert corr >= 0.98 and d_cam <= 1.5e-1
     # trainable parameters received gradients as they do under the reference's autograd; frozen ones none
     assert model.classifier.classifier[0].weight.grad is not None
     assert model.cnn_encoder.backbone.conv1.weight.grad is None
