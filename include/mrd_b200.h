@@ -56,7 +56,9 @@ int mrd_ctx_configure(mrd_ctx* ctx, int img_chunk, int seq_chunk_tokens);
  * "fusion_heads" (8), "fusion_residual" (1), "head_act" (MRD_ACT_RELU).  Set before load_weights.
  * "fuse_ds" (1): run conv3 + downsample of each stage's first bottleneck as one K-concatenated GEMM
  * (mrd_conv1x1_dual_bf16); 0 = separate downsample launch + residual read (A/B switch, same results up to
- * the bf16 rounding of the downsample output that the fused form never materialises). */
+ * the bf16 rounding of the downsample output that the fused form never materialises).
+ * "fuse_chain" (3): bit L-1 set = the tail of every bottleneck of ResNet stage L is chained with the next
+ * block's conv1 in one launch (mrd_conv_chain_bf16); 0 = one launch per convolution. */
 int mrd_ctx_set_option(mrd_ctx* ctx, const char* key, double value);
 
 /* Hands the context the model's fp32 parameters/buffers by their state_dict names
@@ -152,6 +154,18 @@ int mrd_conv2d_nhwc_bf16(const void* X, int N, int H, int W, int Cin, const void
  * The downsample branch's output is never written to memory.  C0, C1, Cout % 64 == 0. */
 int mrd_conv1x1_dual_bf16(const void* X0, int C0, const void* X1, int C1, int stride, int N, int Ho, int Wo,
                           const void* Wcat, int Cout, const float* bias, void* Y, int act, void* stream);
+
+/* Tail of bottleneck i and head of bottleneck i+1 in one launch (TV:143-163 across two blocks):
+ *   Y = relu(X0 * W1[:, :C0]^T (+ X1[:, ::stride, ::stride] * W1[:, C0:]^T) + bias1 (+ identity))
+ *   Z = relu(Y * W2^T + bias2)
+ * X0: [N,Ho,Wo,C0] bf16; X1 (optional, downsample fused; then identity must be NULL): [N,Ho*stride,Wo*stride,C1];
+ * identity (optional): [N,Ho,Wo,Cout]; W1: [Cout][C0(+C1)], W2: [C2][Cout]; Y: [N,Ho,Wo,Cout];
+ * Z: [N,Ho,Wo,C2], or with out_pad = 1 the interior of a zero-bordered [N][Ho+2][Wo+2][C2] tensor.
+ * Y is written once and re-read by the second product while the tile is still in L2: per block one read of the
+ * block's largest tensor from HBM is saved.  Cout % 128 == 0, C2 in {64,128,256}, C0 / C1 % 64 == 0. */
+int mrd_conv_chain_bf16(const void* X0, int C0, const void* X1, int C1, int stride, const void* identity, int N,
+                        int Ho, int Wo, const void* W1, int Cout, const float* bias1, void* Y, const void* W2,
+                        int C2, const float* bias2, void* Z, int out_pad, void* stream);
 
 /* Conv2d(3, stride 1, pad 1) + folded BN + activation in flat-shift mode: Xpad is the zero-bordered
  * [N][H+2][W+2][Cin] bf16 input; the halo span of each tile is fetched once per 64-channel chunk and

@@ -16,7 +16,7 @@ from .multimodal_classifier import (ClassificationHead, ImageOnlyClassifier, Mul
                                     TextOnlyClassifier, create_baseline_classifiers,
                                     create_multimodal_classifier)
 from .optim import FusedAdamW
-from .predict import format_predictions, predict_batch_tensors
+from .predict import collect_predictions, format_predictions, load_checkpoint, predict_batch_tensors
 from .parallel import DataParallelForward, allreduce_mean_, shard_bounds
 from ._lib import MrdError
 

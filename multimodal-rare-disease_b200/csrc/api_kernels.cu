@@ -5,6 +5,7 @@
 
 #include "elementwise.h"
 #include "attention.h"
+#include "conv_chain.h"
 #include "gemm_conv.h"
 #include "tma_host.h"
 
@@ -55,6 +56,18 @@ int mrd_conv1x1_dual_bf16(const void* X0, int C0, const void* X1, int C1, int st
                                static_cast<__nv_bfloat16*>(Y), act);
     if (rc) return rc;
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
+int mrd_conv_chain_bf16(const void* X0, int C0, const void* X1, int C1, int stride, const void* identity, int N,
+                        int Ho, int Wo, const void* W1, int Cout, const float* bias1, void* Y, const void* W2,
+                        int C2, const float* bias2, void* Z, int out_pad, void* stream) {
+    typedef const __nv_bfloat16* cb;
+    ChainLaunch g;
+    int rc = plan_conv_chain(&g, static_cast<cb>(X0), C0, static_cast<cb>(X1), C1, stride, static_cast<cb>(identity), N,
+                             Ho, Wo, static_cast<cb>(W1), Cout, bias1, static_cast<__nv_bfloat16*>(Y),
+                             static_cast<cb>(W2), C2, bias2, static_cast<__nv_bfloat16*>(Z), out_pad);
+    if (rc) return rc;
+    return launch_conv_chain(&g, static_cast<cudaStream_t>(stream));
 }
 
 int mrd_conv3x3_flat_bf16(const void* Xpad, int N, int H, int W, int Cin, const void* Wt, int Cout,

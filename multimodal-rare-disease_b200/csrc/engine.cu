@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "attention.h"
+#include "conv_chain.h"
 #include "elementwise.h"
 #include "fp32_check.h"
 #include "gemm_conv.h"
@@ -80,6 +81,10 @@ struct CnnPlan {
         GemmLaunch c1, c2, c3, ds;
         bool has_ds = false;
         bool fused_ds = false;   // c3 = conv3 + downsample + add (plan_conv1x1_dual); ds is not launched
+        // conv3 (+downsample) + add of THIS block and conv1 of the NEXT block as one launch (conv_chain.h): c3 / ds
+        // of this block and c1 of the next one are then not launched
+        bool chained = false, c1_in_prev_chain = false;
+        ChainLaunch chain;
     };
     std::vector<BlockPlan> blocks;
     const bf16* final_act = nullptr;  // layer4 output [B, H/32*W/32, 2048]
@@ -147,6 +152,7 @@ struct mrd_ctx {
     int fusion_residual = 1;
     int head_act = MRD_ACT_RELU;
     int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
+    int fuse_chain = 0;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
     TrainState* train = nullptr;   // training step state (engine_train.cuh), created on first use
@@ -681,6 +687,26 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
             MRD_TRY(plan_conv(&bp.c3, c->mid1, B, ho, wo, b.c3.cin, b.c3.w, b.c3.cout, b.c3.k, 1,
                               b.c3.b, y, identity, ACT_RELU));
         }
+        // ---- chain this block's tail with the next block's conv1 (same pixels, one launch, y re-read from L2)
+        if (i + 1 < c->blocks.size() && (c->fuse_chain >> (c->block_stage[i] - 1) & 1)) {
+            const Bottleneck& nx = c->blocks[i + 1];
+            const bool dual = b.has_ds && b.c3ds_w != nullptr;
+            const bool ok = b.c3.k == 1 && nx.c1.k == 1 && nx.c1.stride == 1 && nx.c1.cin == b.c3.cout &&
+                            (!b.has_ds || dual) &&
+                            conv_chain_supported(b.c3.cin, dual ? b.ds.cin : 0, b.c3.cout, nx.c1.cout);
+            if (ok) {
+                bf16* npad = nullptr;   // the next block's conv1 writes into its flat-3x3 input when it has one
+                if (flat3_eligible(nx.c2, ho, wo))
+                    for (auto& pb : c->pads)
+                        if (pb.h == ho && pb.w == wo && pb.c == nx.c2.cin) npad = pb.p;
+                MRD_TRY(plan_conv_chain(&bp.chain, c->mid1, b.c3.cin, dual ? x : nullptr, dual ? b.ds.cin : 0,
+                                        b.ds.stride, dual ? nullptr : x, B, ho, wo, dual ? b.c3ds_w : b.c3.w,
+                                        b.c3.cout, dual ? b.c3ds_b : b.c3.b, y, nx.c1.w, nx.c1.cout, nx.c1.b,
+                                        npad ? npad : c->mid0, npad ? 1 : 0));
+                bp.chained = true;
+                p.blocks[i + 1].c1_in_prev_chain = true;
+            }
+        }
         x = y;
         cur ^= 1;
         h = ho;
@@ -945,9 +971,15 @@ int run_backbone(mrd_ctx* c, const void* images, int img_dtype, int B, int H, in
         for (size_t i = 0; i < p->blocks.size(); ++i) {
             auto& bp = p->blocks[i];
             const char* st = kStage[c->block_stage[i]];
-            MRD_TRY(run(c, c->label(st, ".conv1_1x1"), bp.c1, s));
+            if (!bp.c1_in_prev_chain) MRD_TRY(run(c, c->label(st, ".conv1_1x1"), bp.c1, s));
             MRD_TRY(run(c, c->label(st, c->blocks[i].c2.stride == 2 ? ".conv2_3x3s2" : ".conv2_3x3"),
                         bp.c2, s));
+            if (bp.chained) {
+                ProfScope ps(c, s, c->label(st, bp.has_ds ? ".conv3+ds+next_conv1" : ".conv3+res+next_conv1"),
+                             CAT_TENSOR, bp.chain.flops, bp.chain.bytes);
+                MRD_TRY(launch_conv_chain(&bp.chain, s));
+                continue;
+            }
             if (bp.fused_ds) {
                 MRD_TRY(run(c, c->label(st, ".conv3+downsample"), bp.c3, s));
                 continue;
@@ -1237,6 +1269,11 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
+    else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }
+    else if (k == "chain_tuning") {   // process-wide A/B switch: value = lag * 8 + hints (conv_chain.h)
+        conv_chain_set_tuning(static_cast<int>(v) / 8, static_cast<int>(v) % 8);
+        c->cnn_plans.clear();
+    }
     else if (k == "load_sync") c->load_sync = v != 0.0;
     else if (k.rfind("train.", 0) == 0) return train_set_option(c, k, v);
     else {

@@ -115,6 +115,35 @@ __device__ __forceinline__ void tma_load_5d(const void* map, uint32_t bar, uint3
         : "memory");
 }
 
+// L2 eviction-priority hints for TMA traffic: streaming operands (read once) should not push out a tile that is
+// about to be re-read; a tile that WILL be re-read soon is stored with evict_last.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(const void* map, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                 int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const void* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::
+            "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+
 // L2 prefetch of a tensor box (no shared-memory destination, no barrier): used by producers that
 // hold only a few large stages to pull the tiles they will need next from HBM into L2.
 __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {

@@ -212,8 +212,6 @@ class Engine:
         emb = self._f32(B, emb_dim)
         pooled = self._f32(B, 2048) if want_pooled else None
         fmap = self._f32(B, 2048, H // 32, W // 32) if want_map else None
-        embs = [self._f32(B, d) for d in emb_dims] if emb_dims else [None, None, None]
-        self.last_train_embeddings = embs if emb_dims else None
         if B:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.mrd_cnn_encoder_fwd(self._ctx, images.data_ptr(), code, B, H, W,

@@ -10,7 +10,8 @@ formatted exactly like `MultimodalPredictor.predict_batch` (src/predict.py:199-2
 
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import torch
 
@@ -62,3 +63,60 @@ def predict_batch_tensors(model, images: torch.Tensor, input_ids: torch.Tensor,
     finally:
         for m, flag in modes:
             m.training = flag
+
+
+def load_checkpoint(model, checkpoint_path: Union[str, Path], strict: bool = True) -> Dict:
+    """`MultimodalPredictor._load_checkpoint` (src/predict.py:73-82): reads a checkpoint written by the reference's
+    trainers (src/train.py:394-437: {"model_state_dict": ..., "optimizer_state_dict": ..., ...}) - or a bare
+    state_dict - into the drop-in model.  The state_dict keys are the reference's own, so nothing is renamed; the
+    library's packed bf16 weights are rebuilt on the next forward (the parameters' version counters changed).
+    Returns the checkpoint dict (epoch, metrics, optimizer state for a caller that resumes training)."""
+    path = Path(checkpoint_path)
+    if not path.exists():
+        raise FileNotFoundError(f"Checkpoint not found: {path}")     # src/predict.py:77-78
+    ckpt = torch.load(path, map_location="cpu")
+    sd = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt
+    model.load_state_dict(sd, strict=strict)
+    return ckpt if isinstance(ckpt, dict) else {"model_state_dict": sd}
+
+
+@torch.no_grad()
+def collect_predictions(model, loader: Iterable, mode: str = "multimodal", device=None,
+                        micro_batch: int = 512) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """`Evaluator.collect_predictions` (src/evaluate.py:79-123) on the B200 path: walks a loader of the reference's
+    batch dicts ({"image", "input_ids", "attention_mask", "label"}; image_only loaders may yield (image, label)
+    tuples) and returns (predictions i64 [N], true_labels i64 [N], probabilities f32 [N,C]) on the host - the three
+    arrays the reference's compute_metrics / confusion-matrix code consumes.
+    Host batches of the multimodal mode go through `forward_host` (H2D of micro-batch i+1 under the kernels of
+    micro-batch i); argmax runs on the device and one transfer per batch brings predictions and probabilities back."""
+    if mode not in ("multimodal", "image_only", "text_only"):
+        raise ValueError(f"Unknown mode: {mode}")
+    modes = [(m, m.training) for m in model.modules()]
+    model.eval()
+    dev = torch.device(device) if device is not None else next(model.parameters()).device
+    preds, labels, probs = [], [], []
+    try:
+        for batch in loader:
+            if mode == "multimodal":
+                images, ids, mask, y = batch["image"], batch["input_ids"], batch["attention_mask"], batch["label"]
+                if images.device.type == "cpu" and hasattr(model, "forward_host"):
+                    out = model.forward_host(images, ids, mask, micro_batch=micro_batch)
+                else:
+                    out = model(images.to(dev), ids.to(dev), mask.to(dev))
+            elif mode == "image_only":
+                images, y = (batch[0], batch[1]) if isinstance(batch, (tuple, list)) else (batch["image"], batch["label"])
+                out = model(images.to(dev))
+            else:
+                y = batch["label"]
+                out = model(batch["input_ids"].to(dev), batch["attention_mask"].to(dev))
+            p = out["probs"]
+            both = torch.cat([out["logits"].argmax(dim=-1, keepdim=True).to(p.dtype), p], dim=1).cpu()
+            preds.append(both[:, 0].long())
+            probs.append(both[:, 1:])
+            labels.append(y.detach().cpu().long() if torch.is_tensor(y) else torch.as_tensor(list(y), dtype=torch.long))
+    finally:
+        for m, flag in modes:
+            m.training = flag
+    if not preds:
+        return torch.empty(0, dtype=torch.long), torch.empty(0, dtype=torch.long), torch.empty(0, 0)
+    return torch.cat(preds), torch.cat(labels), torch.cat(probs)

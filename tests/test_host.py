@@ -325,3 +325,46 @@ def test_weight_handover_groups(model):
     # the frozen backbone is exactly the group a default-configuration training step never re-packs
     assert not any(t.requires_grad for _, t in groups["cnn_encoder.backbone."])
     assert all(t.requires_grad for _, t in groups["cnn_encoder.projection."])
+
+
+def test_collect_predictions_and_checkpoint_loader(tmp_path):
+    """collect_predictions == Evaluator.collect_predictions (src/evaluate.py:79-123) on any model with the reference's
+    output dict; load_checkpoint == MultimodalPredictor._load_checkpoint (src/predict.py:73-82)."""
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3 * 4 * 4, 5)
+
+        def forward(self, images, input_ids=None, attention_mask=None):
+            logits = self.lin(images.flatten(1))
+            if input_ids is not None:
+                logits = logits + input_ids[:, :5].float() * attention_mask[:, :5].float()
+            return {"logits": logits, "probs": torch.softmax(logits, -1)}
+
+    torch.manual_seed(3)
+    m = Tiny().train()
+    batches = [{"image": torch.randn(4, 3, 4, 4), "input_ids": torch.randint(0, 9, (4, 6)),
+                "attention_mask": torch.ones(4, 6, dtype=torch.long), "label": torch.tensor([0, 1, 2, 3])},
+               {"image": torch.randn(2, 3, 4, 4), "input_ids": torch.randint(0, 9, (2, 6)),
+                "attention_mask": torch.ones(2, 6, dtype=torch.long), "label": [4, 0]}]
+    preds, labels, probs = mrd_b200.collect_predictions(m, batches, mode="multimodal", device="cpu")
+    assert m.training                                    # the caller's mode flags are restored
+    assert preds.shape == (6,) and labels.tolist() == [0, 1, 2, 3, 4, 0] and probs.shape == (6, 5)
+    with torch.no_grad():
+        want = torch.cat([m.eval()(b["image"], b["input_ids"], b["attention_mask"])["probs"] for b in batches])
+    assert torch.allclose(probs, want) and torch.equal(preds, want.argmax(-1))
+    p2, l2, _ = mrd_b200.collect_predictions(m, [(b["image"], b["label"]) for b in batches[:1]], mode="image_only",
+                                             device="cpu")
+    assert p2.shape == (4,) and l2.tolist() == [0, 1, 2, 3]
+    with pytest.raises(ValueError, match="Unknown mode"):
+        mrd_b200.collect_predictions(m, batches, mode="audio")
+    # checkpoints as src/train.py:394-437 writes them, and bare state_dicts
+    path = tmp_path / "best_model.pt"
+    torch.save({"model_state_dict": m.state_dict(), "epoch": 7}, path)
+    fresh = Tiny()
+    ck = mrd_b200.load_checkpoint(fresh, path)
+    assert ck["epoch"] == 7 and torch.equal(fresh.lin.weight, m.lin.weight)
+    torch.save(m.state_dict(), tmp_path / "bare.pt")
+    mrd_b200.load_checkpoint(Tiny(), tmp_path / "bare.pt")
+    with pytest.raises(FileNotFoundError, match="Checkpoint not found"):
+        mrd_b200.load_checkpoint(fresh, tmp_path / "missing.pt")

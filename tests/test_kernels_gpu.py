@@ -193,6 +193,48 @@ def test_conv1x1_dual(lib, cuda, N, Ho, Wo, C0, C1, Cout, stride):
     _close(y.permute(0, 3, 1, 2), ref, what=f"dual 1x1 conv {C0}+{C1}->{Cout} stride {stride}")
 
 
+@pytest.mark.parametrize("N,Ho,Wo,C0,C1,stride,Cout,C2,out_pad", [
+    (3, 56, 56, 64, 0, 1, 256, 64, 1),       # layer1.1 -> layer1.2: identity, padded output, pixel-box tiles
+    (2, 56, 56, 64, 64, 1, 256, 64, 1),      # layer1.0 (downsample fused) -> layer1.1
+    (3, 56, 56, 64, 0, 1, 256, 128, 0),      # layer1.2 -> layer2.0: unpadded output, flat tiles
+    (2, 28, 28, 128, 256, 2, 512, 128, 1),   # layer2.0 (stride-2 downsample fused) -> layer2.1
+    (5, 28, 28, 128, 0, 1, 512, 128, 1),     # layer2.1 -> layer2.2
+    (4, 14, 14, 256, 0, 1, 1024, 256, 0),    # layer3: two N tiles in the second product
+    (300, 28, 28, 128, 0, 1, 512, 128, 1),   # many tiles per CTA: pipeline wrap-around, y hand-off ring
+    (1, 6, 10, 64, 0, 1, 128, 64, 0),        # fewer tiles than the hand-off lag
+])
+def test_conv_chain(lib, cuda, N, Ho, Wo, C0, C1, stride, Cout, C2, out_pad):
+    """conv3 (+downsample) + identity + ReLU of one bottleneck and conv1 + ReLU of the next in one launch."""
+    g = torch.Generator(device="cuda").manual_seed(Ho * Wo + Cout + C1)
+    x0 = torch.randn(N, Ho, Wo, C0, device=cuda, generator=g).to(BF)
+    x1 = torch.randn(N, Ho * stride, Wo * stride, C1, device=cuda, generator=g).to(BF) if C1 else None
+    ident = None if C1 else torch.randn(N, Ho, Wo, Cout, device=cuda, generator=g).to(BF)
+    w1 = (torch.randn(Cout, C0 + C1, device=cuda, generator=g) / math.sqrt(C0 + C1)).to(BF)
+    b1 = torch.randn(Cout, device=cuda, generator=g)
+    w2 = (torch.randn(C2, Cout, device=cuda, generator=g) / math.sqrt(Cout)).to(BF)
+    b2 = torch.randn(C2, device=cuda, generator=g)
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=cuda, dtype=BF)
+    z = torch.zeros(N, Ho + 2 * out_pad, Wo + 2 * out_pad, C2, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_conv_chain_bf16(x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, stride,
+                                        ident.data_ptr() if ident is not None else None, N, Ho, Wo, w1.data_ptr(),
+                                        Cout, b1.data_ptr(), y.data_ptr(), w2.data_ptr(), C2, b2.data_ptr(),
+                                        z.data_ptr(), out_pad, _stream()))
+    torch.cuda.synchronize()
+    acc = x0.float().reshape(-1, C0) @ w1.float()[:, :C0].t()
+    if C1:
+        acc = acc + x1[:, ::stride, ::stride].float().reshape(-1, C1) @ w1.float()[:, C0:].t()
+    acc = acc + b1
+    if ident is not None:
+        acc = acc + ident.float().reshape(-1, Cout)
+    y_ref = F.relu(acc)
+    _close(y.reshape(-1, Cout), y_ref, what="chain: block output y")
+    z_ref = F.relu(y.float().reshape(-1, Cout) @ w2.float().t() + b2)   # from the bf16 y the kernel itself re-reads
+    zi = z[:, out_pad:out_pad + Ho, out_pad:out_pad + Wo] if out_pad else z
+    _close(zi.reshape(-1, C2), z_ref, what="chain: next conv1 output z")
+    if out_pad:
+        assert (z[:, 0] == 0).all() and (z[:, -1] == 0).all() and (z[:, :, 0] == 0).all() and (z[:, :, -1] == 0).all()
+
+
 def test_conv3x3_flat_rejects_unsupported(lib, cuda):
     # the resident 3x3 weight panel of Cin=128 does not fit next to two 56-wide halo spans
     x = torch.zeros(1, 58, 58, 128, device=cuda, dtype=BF)
