@@ -152,7 +152,7 @@ struct mrd_ctx {
     int fusion_residual = 1;
     int head_act = MRD_ACT_RELU;
     int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
-    int fuse_chain = 0;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
+    int fuse_chain = 1;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
     TrainState* train = nullptr;   // training step state (engine_train.cuh), created on first use
@@ -1270,6 +1270,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }
+    else if (k == "split_epilogue") gemm_set_split_epilogue(static_cast<int>(v));   // process-wide A/B switch
     else if (k == "chain_tuning") {   // process-wide A/B switch: value = lag * 8 + hints (conv_chain.h)
         conv_chain_set_tuning(static_cast<int>(v) / 8, static_cast<int>(v) % 8);
         c->cnn_plans.clear();

@@ -30,6 +30,7 @@ namespace mrd {
 namespace {
 
 bool g_use_pdl = true;
+int g_split_epilogue = 1;   // two-group epilogue (EPI2): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem
 
 constexpr int kBlockM = 128;
 constexpr int kNumThreads = 352;  // TMA warp + MMA warp + 8 epilogue warps + residual-loader warp
@@ -80,7 +81,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 //   [stages x A_STAGE][stages x B_STAGE][2 x 16 KB store staging][ring x 16 KB residual][barriers]
 // SPLITK (generic mode only) is a separate instantiation so that the forward's kernels compile exactly as they
 // did before split-K existed: measured, the merged version cost the forward 3 % (different epilogue schedule).
-template <int BLOCK_N, int MODE, bool SPLITK = false>
+// EPI2: the eight epilogue warps work as two independent groups of four (one warp per TMEM lane quarter each); group g
+// takes the 64-column sub-tiles with q % 2 == g of the CTA's sub-tile sequence and a thread owns one row and all 64
+// columns.  A sub-tile is a latency chain (TMEM load -> residual -> activation -> pack -> proxy fence -> barrier ->
+// TMA store, ~1500 cycles measured on the chained bottleneck kernel of conv_chain.cu): with one sub-tile in flight
+// per CTA that chain bounds every launch whose main loop is shorter than it.
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BLOCK_N, MODE>;
@@ -132,11 +138,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             mbar_init(rfull_bar(s), 1);
-            mbar_init(rempty_bar(s), 8);  // one arrival per epilogue warp
+            mbar_init(rempty_bar(s), EPI2 ? 4 : 8);  // one arrival per epilogue warp that consumed the sub-tile
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp
+            // one arrival per epilogue warp and accumulator (EPI2: four warps per 64-column sub-tile)
+            mbar_init(tempty_bar(a), EPI2 ? 4 * (BLOCK_N / 64) : 8);
         }
         mbar_init(bres_bar, 1);
         fence_mbar_init();
@@ -390,6 +397,111 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 }
             }
         }
+    } else if (EPI2) {
+        // ------------------------------------------------------------ epilogue, two groups of four warps
+        const int grp = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;   // issues this group's TMA stores
+        const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;        // this group's named barriers (128 threads)
+        const int wi = row % p.tw;
+        const int hi = (row / p.tw) % p.th;
+        const int ni = row / (p.tw * p.th);
+        const bool has_res = p.has_res != 0;
+        const int nq = my_tiles * NSUB;
+        uint8_t* st_row = st_gen + grp * kStageBufBytes + row * 128;   // one staging buffer per group
+        for (int q = grp; q < nq; q += 2) {
+            const int sub = q % NSUB;
+            const int it = q / NSUB;
+            const int acc = it & 1;
+            const TileCoord t = decode_tile(p, bid + it * nblk);
+            const int col0 = t.n_idx * BLOCK_N + sub * 64;
+            mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + sub * 64;
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            float f[64];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (p.bias) {
+                    b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
+                }
+                f[j + 0] = __uint_as_float(v0[j + 0]) + b0.x;
+                f[j + 1] = __uint_as_float(v0[j + 1]) + b0.y;
+                f[j + 2] = __uint_as_float(v0[j + 2]) + b0.z;
+                f[j + 3] = __uint_as_float(v0[j + 3]) + b0.w;
+                f[32 + j + 0] = __uint_as_float(v1[j + 0]) + b1.x;
+                f[32 + j + 1] = __uint_as_float(v1[j + 1]) + b1.y;
+                f[32 + j + 2] = __uint_as_float(v1[j + 2]) + b1.z;
+                f[32 + j + 3] = __uint_as_float(v1[j + 3]) + b1.w;
+            }
+            if (has_res) {   // the loader fetched the residual sub-tiles in q order
+                const int rslot = q % RING;
+                mbar_wait(rfull_bar(rslot), static_cast<uint32_t>(q / RING) & 1u);
+                const uint8_t* r_row = ring_gen + rslot * kStageBufBytes + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(r_row + ((c ^ (row & 7)) << 4));
+                    const float2 r0 = unpack_bf16(r4.x), r1 = unpack_bf16(r4.y),
+                                 r2 = unpack_bf16(r4.z), r3 = unpack_bf16(r4.w);
+                    f[c * 8 + 0] += r0.x; f[c * 8 + 1] += r0.y;
+                    f[c * 8 + 2] += r1.x; f[c * 8 + 3] += r1.y;
+                    f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
+                    f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty_bar(rslot));
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) f[j] = gelu_erf_fast(f[j]);
+            }
+            if (p.out_f32) {
+                const bool row_ok = (row < box_rows) && (t.n0 + ni < p.Nimg) && (t.h0 + hi < p.Ho) &&
+                                    (t.w0 + wi < p.Wo);
+                if (row_ok) {
+                    const long long pix =
+                        (static_cast<long long>(t.n0 + ni) * p.Ho + (t.h0 + hi)) * p.Wo + (t.w0 + wi);
+                    float* f32_row = p.out_f32 + pix * p.ld_f32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4)
+                        *reinterpret_cast<float4*>(f32_row + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+            }
+            // this group's staging buffer was the source of its previous TMA store: it must have been read
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(bar_b, 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 o;
+                o.x = pack_bf16(f[c * 8 + 0], f[c * 8 + 1]);
+                o.y = pack_bf16(f[c * 8 + 2], f[c * 8 + 3]);
+                o.z = pack_bf16(f[c * 8 + 4], f[c * 8 + 5]);
+                o.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
+                *reinterpret_cast<uint4*>(st_row + ((c ^ (row & 7)) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_a, 128);
+            if (leader && p.store_bf16) {
+                if (p.c_blocked)
+                    tma_store_4d(&p.c_map, st_smem + grp * kStageBufBytes, 0, t.w0, t.n_idx * NSUB + sub, 0);
+                else
+                    tma_store_4d(&p.c_map, st_smem + grp * kStageBufBytes, col0, t.w0, t.h0, t.n0);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_all<0>();
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         const int quarter = warp & 3;           // TMEM lane quarter this warp may access
@@ -520,11 +632,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
 }
 
-template <int BLOCK_N, int MODE, bool SPLITK = false>
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false>
 int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
-    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK>;
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK, EPI2>;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -636,6 +748,7 @@ int finish_plan(GemmLaunch* g, int block_n) {
 }  // namespace
 
 void gemm_set_pdl(bool on) { g_use_pdl = on; }
+void gemm_set_split_epilogue(int mask) { g_split_epilogue = mask; }
 
 int gemm_num_sms() {
     static int sms = 0;
@@ -1128,7 +1241,16 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
 }
 
 int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
-    if (g->stem) return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
+    if (g->stem) {
+        if (g_split_epilogue & 4) return launch_variant<64, MODE_STEM, false, true>(g, stream, sm_limit);
+        return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
+    }
+    if (g->flat3 && (g_split_epilogue & 2)) {
+        switch (g->block_n) {
+            case 64: return launch_variant<64, MODE_FLAT3, false, true>(g, stream, sm_limit);
+            case 128: return launch_variant<128, MODE_FLAT3, false, true>(g, stream, sm_limit);
+        }
+    }
     if (g->flat3) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_FLAT3>(g, stream, sm_limit);
@@ -1142,6 +1264,13 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
             case 64: return launch_variant<64, MODE_GENERIC, true>(g, stream, sm_limit);
             case 128: return launch_variant<128, MODE_GENERIC, true>(g, stream, sm_limit);
             case 256: return launch_variant<256, MODE_GENERIC, true>(g, stream, sm_limit);
+        }
+    }
+    if (g_split_epilogue & 1) {
+        switch (g->block_n) {
+            case 64: return launch_variant<64, MODE_GENERIC, false, true>(g, stream, sm_limit);
+            case 128: return launch_variant<128, MODE_GENERIC, false, true>(g, stream, sm_limit);
+            case 256: return launch_variant<256, MODE_GENERIC, false, true>(g, stream, sm_limit);
         }
     }
     switch (g->block_n) {

@@ -125,5 +125,7 @@ int gemm_num_sms();
 // Programmatic dependent launch for the GEMM/conv kernels (on by default; the engine turns it off
 // while profiling so that per-launch event timings do not overlap).
 void gemm_set_pdl(bool on);
+// Two-group epilogue (process-wide A/B switch): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem.
+void gemm_set_split_epilogue(int mask);
 
 }  // namespace mrd

@@ -156,7 +156,9 @@ def test_hooks_removed_restores_the_plain_eval_path(cuda):
     assert (out.detach() - ref).abs().max().item() <= 2e-2   # fp32 batch-level layers vs bf16 ones
     with torch.no_grad():                                     # forward hooks fire without autograd as well
         out_ng = model(images, ids, mask)["logits"]
-    assert not out_ng.requires_grad and torch.equal(out_ng, out.detach()) and len(seen) == 2
+    # (the fp32 batch-level GEMMs of this path reduce split-K partial sums with atomics: equal to rounding, not bitwise)
+    assert not out_ng.requires_grad and len(seen) == 2
+    assert (out_ng - out.detach()).abs().max().item() <= 1e-5
     h.remove()
     out2 = model(images, ids, mask)["logits"]
     assert not out2.requires_grad and torch.equal(out2, ref)

@@ -197,11 +197,10 @@ def test_conv1x1_dual(lib, cuda, N, Ho, Wo, C0, C1, Cout, stride):
     (3, 56, 56, 64, 0, 1, 256, 64, 1),       # layer1.1 -> layer1.2: identity, padded output, pixel-box tiles
     (2, 56, 56, 64, 64, 1, 256, 64, 1),      # layer1.0 (downsample fused) -> layer1.1
     (3, 56, 56, 64, 0, 1, 256, 128, 0),      # layer1.2 -> layer2.0: unpadded output, flat tiles
-    (2, 28, 28, 128, 256, 2, 512, 128, 1),   # layer2.0 (stride-2 downsample fused) -> layer2.1
-    (5, 28, 28, 128, 0, 1, 512, 128, 1),     # layer2.1 -> layer2.2
-    (4, 14, 14, 256, 0, 1, 1024, 256, 0),    # layer3: two N tiles in the second product
-    (300, 28, 28, 128, 0, 1, 512, 128, 1),   # many tiles per CTA: pipeline wrap-around, y hand-off ring
-    (1, 6, 10, 64, 0, 1, 128, 64, 0),        # fewer tiles than the hand-off lag
+    (2, 28, 28, 64, 64, 2, 256, 64, 1),      # stride-2 downsample fused
+    (130, 28, 28, 64, 0, 1, 256, 128, 1),    # many tiles per CTA: staging-ring and accumulator wrap-around
+    (1, 6, 10, 64, 0, 1, 128, 64, 0),        # a single tile
+    (2, 9, 7, 128, 0, 1, 128, 64, 1),        # two K chunks in the first product, two images per tile
 ])
 def test_conv_chain(lib, cuda, N, Ho, Wo, C0, C1, stride, Cout, C2, out_pad):
     """conv3 (+downsample) + identity + ReLU of one bottleneck and conv1 + ReLU of the next in one launch."""
@@ -233,6 +232,15 @@ def test_conv_chain(lib, cuda, N, Ho, Wo, C0, C1, stride, Cout, C2, out_pad):
     _close(zi.reshape(-1, C2), z_ref, what="chain: next conv1 output z")
     if out_pad:
         assert (z[:, 0] == 0).all() and (z[:, -1] == 0).all() and (z[:, :, 0] == 0).all() and (z[:, :, -1] == 0).all()
+
+
+def test_conv_chain_rejects_what_does_not_fit(lib, cuda):
+    """Both weight matrices stay resident in shared memory: layer2-sized pairs (2 x 128 KB) are refused and the
+    engine keeps one launch per convolution there."""
+    x = torch.zeros(1, 28, 28, 512, device=cuda, dtype=BF)
+    rc = lib.mrd_conv_chain_bf16(x.data_ptr(), 128, None, 0, 1, x.data_ptr(), 1, 28, 28, x.data_ptr(), 512, None,
+                                 x.data_ptr(), x.data_ptr(), 128, None, x.data_ptr(), 0, _stream())
+    assert rc != 0 and b"shared memory" in lib.mrd_last_error()
 
 
 def test_conv3x3_flat_rejects_unsupported(lib, cuda):

@@ -42,7 +42,7 @@ def timed(fn):
 
 
 for name, (N, H, W, C0, Cout, C2, pad) in {"layer1": (512, 56, 56, 64, 256, 64, 1),
-                                           "layer2": (512, 28, 28, 128, 512, 128, 1)}.items():
+                                           "layer1->2": (512, 56, 56, 64, 256, 128, 0)}.items():
     g = torch.Generator(device="cuda").manual_seed(1)
     x0 = torch.randn(N, H, W, C0, device=dev, generator=g).to(BF)
     ident = torch.randn(N, H, W, Cout, device=dev, generator=g).to(BF)
