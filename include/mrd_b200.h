@@ -57,7 +57,8 @@ int mrd_ctx_configure(mrd_ctx* ctx, int img_chunk, int seq_chunk_tokens);
  * "fuse_ds" (1): run conv3 + downsample of each stage's first bottleneck as one K-concatenated GEMM
  * (mrd_conv1x1_dual_bf16); 0 = separate downsample launch + residual read (A/B switch, same results up to
  * the bf16 rounding of the downsample output that the fused form never materialises).
- * "fuse_chain" (3): bit L-1 set = the tail of every bottleneck of ResNet stage L is chained with the next
+ * "fuse_pool" (1): the stem launch also does the max pooling (mrd_stem_pool_bf16); 0 = separate pooling pass.
+ * "fuse_chain" (1): bit L-1 set = the tail of every bottleneck of ResNet stage L is chained with the next
  * block's conv1 in one launch (mrd_conv_chain_bf16); 0 = one launch per convolution. */
 int mrd_ctx_set_option(mrd_ctx* ctx, const char* key, double value);
 
@@ -177,6 +178,12 @@ int mrd_conv3x3_flat_bf16(const void* Xpad, int N, int H, int W, int Cin, const 
  * Xpad [N][H+6][W+8][4] bf16; Wst [64][7][32] bf16; Y [N,H/2,W/2,64] bf16. */
 int mrd_stem_conv_bf16(const void* Xpad, int N, int H, int W, const void* Wst, const float* bias,
                        void* Y, int act, void* stream);
+
+/* The stem with MaxPool2d(3, stride 2, pad 1) (TV:200,271) fused into its epilogue: P [N,H/4,W/4,64] bf16.
+ * P must be ZERO when the launch starts (window maxima are folded into it with red.global.max); the 112 x 112 stem
+ * output is never written.  H % 32 == 0, W % 32 == 0. */
+int mrd_stem_pool_bf16(const void* Xpad, int N, int H, int W, const void* Wst, const float* bias, void* P,
+                       void* stream);
 
 /* [N,3,H,W] (f32 or bf16) -> Xpad [N][H+6][W+8][4] bf16, pixel (h,w) at (h+3,w+3), zero elsewhere. */
 int mrd_repack_images(const void* x_nchw, int img_dtype, int N, int H, int W, void* xpad,

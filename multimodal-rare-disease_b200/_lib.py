@@ -52,6 +52,7 @@ SIGNATURES = {
     "mrd_conv_chain_bf16": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "mrd_conv3x3_flat_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "mrd_stem_conv_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "mrd_stem_pool_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mrd_repack_images": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mrd_maxpool3x3s2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mrd_global_avgpool": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

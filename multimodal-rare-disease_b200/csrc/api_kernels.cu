@@ -90,6 +90,15 @@ int mrd_stem_conv_bf16(const void* Xpad, int N, int H, int W, const void* Wst, c
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }
 
+int mrd_stem_pool_bf16(const void* Xpad, int N, int H, int W, const void* Wst, const float* bias, void* P,
+                       void* stream) {
+    GemmLaunch g;
+    int rc = plan_stem_pool(&g, static_cast<const __nv_bfloat16*>(Xpad), N, H, W,
+                            static_cast<const __nv_bfloat16*>(Wst), bias, static_cast<__nv_bfloat16*>(P));
+    if (rc) return rc;
+    return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
 int mrd_repack_images(const void* x_nchw, int img_dtype, int N, int H, int W, void* xpad,
                       void* stream) {
     if (img_dtype != MRD_DT_F32 && img_dtype != MRD_DT_BF16) {

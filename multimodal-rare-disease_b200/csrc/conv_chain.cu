@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_co
             mbar_init(sfull(s), 1);
             mbar_init(sdone(s), 1);
             mbar_init(rfull(s), 1);
-            mbar_init(rempty(s), 4);   // one arrival per warp of the epilogue group that consumed the sub-tile
+            mbar_init(rempty(s), 1);   // one arrival per consumed sub-tile, by the group's leader (see sub_tile)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull1(a), 1);
@@ -302,8 +302,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_co
                     f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
                     f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rempty(rslot));
             }
             if (P.act == ACT_RELU) {
 #pragma unroll
@@ -329,6 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_co
             fence_proxy_async_smem();
             named_bar_sync(bar_a, 128);
             if (leader) {
+                // The identity slot is released only here, after every thread of the group has stored values that
+                // depend on its ld.shared of the slot: an arrive right after the loads does not wait for them, and
+                // the loader's next TMA write overtook loads still in flight (tools/stress_patterns.py, r02).
+                if (yq >= 0) mbar_arrive(rempty(yq % RING));
                 tma_store_4d(&P.c_map, st_s + slot * kSub, col0, t.w0, t.h0, t.n0);
                 tma_store_commit();
                 mbar_arrive(sfull(slot));

@@ -77,6 +77,7 @@ struct BertLayerW {
 struct CnnPlan {
     int B = 0, H = 0, W = 0;
     GemmLaunch stem;
+    bool pooled_stem = false;   // stem launch = conv + BN + ReLU + maxpool (plan_stem_pool)
     struct BlockPlan {
         GemmLaunch c1, c2, c3, ds;
         bool has_ds = false;
@@ -152,6 +153,7 @@ struct mrd_ctx {
     int fusion_residual = 1;
     int head_act = MRD_ACT_RELU;
     int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
+    int fuse_pool = 1;     // MaxPool2d(3,2,1) fused into the stem's epilogue (plan_stem_pool)
     int fuse_chain = 1;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
@@ -639,7 +641,11 @@ int get_cnn_plan(mrd_ctx* c, int B, int H, int W, CnnPlan** out) {
     }
     CnnPlan p;
     p.B = B; p.H = H; p.W = W;
-    MRD_TRY(plan_stem(&p.stem, c->xpad, B, H, W, c->stem_w, c->stem_b, c->stem_out, ACT_RELU));
+    if (c->fuse_pool)   // stem + BN + ReLU + maxpool in one launch: the pooled map goes straight to act0
+        MRD_TRY(plan_stem_pool(&p.stem, c->xpad, B, H, W, c->stem_w, c->stem_b, c->act0));
+    else
+        MRD_TRY(plan_stem(&p.stem, c->xpad, B, H, W, c->stem_w, c->stem_b, c->stem_out, ACT_RELU));
+    p.pooled_stem = c->fuse_pool != 0;
     int h = H / 4, w = W / 4;
     const bf16* x = c->act0;  // maxpool output goes to act0
     bf16* bufs[2] = {c->act0, c->act1};
@@ -963,8 +969,18 @@ int run_backbone(mrd_ctx* c, const void* images, int img_dtype, int B, int H, in
                          1.0 * nb * (3.0 * H * W * esz + (H + 6.0) * (W + 8) * 8));
             MRD_TRY(repack_images(img, img_dtype == MRD_DT_BF16, nb, H, W, c->xpad, s));
         }
-        MRD_TRY(run(c, "conv_stem7x7", p->stem, s));
-        {
+        if (p->pooled_stem) {
+            // the epilogue folds partial window maxima into act0 with red.global.max: start from zero (= the padding
+            // value and the identity of the maximum of post-ReLU values)
+            const size_t pooled_bytes = static_cast<size_t>(nb) * (H / 4) * (W / 4) * 64 * sizeof(bf16);
+            {
+                ProfScope ps(c, s, "zero_pooled", CAT_MEM, 0, 1.0 * pooled_bytes);
+                cudaError_t e = cudaMemsetAsync(c->act0, 0, pooled_bytes, s);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(pooled stem output)");
+            }
+            MRD_TRY(run(c, "conv_stem7x7+maxpool", p->stem, s));
+        } else {
+            MRD_TRY(run(c, "conv_stem7x7", p->stem, s));
             ProfScope ps(c, s, "maxpool3x3s2", CAT_MEM, 0, 1.0 * nb * (H / 2) * (W / 2) * 64 * 2 * 1.25);
             MRD_TRY(maxpool3x3s2(c->stem_out, nb, H / 2, W / 2, 64, c->act0, s));
         }
@@ -1269,6 +1285,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
+    else if (k == "fuse_pool") { c->fuse_pool = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }
     else if (k == "split_epilogue") gemm_set_split_epilogue(static_cast<int>(v));   // process-wide A/B switch
     else if (k == "chain_tuning") {   // process-wide A/B switch: value = lag * 8 + hints (conv_chain.h)

@@ -20,6 +20,7 @@
 #include "gemm_conv.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -30,7 +31,18 @@ namespace mrd {
 namespace {
 
 bool g_use_pdl = true;
-int g_split_epilogue = 1;   // two-group epilogue (EPI2): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem
+int g_split_epilogue = 3;   // two-group epilogue (EPI2): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem
+
+// Debugging overrides (tools/stress_kernels.py): MRD_DEBUG_SPLIT_EPILOGUE, MRD_DEBUG_PDL, MRD_DEBUG_RING, read once.
+int g_debug_ring = -1;
+void apply_debug_env() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char* e = getenv("MRD_DEBUG_SPLIT_EPILOGUE")) g_split_epilogue = atoi(e);
+    if (const char* e = getenv("MRD_DEBUG_PDL")) g_use_pdl = atoi(e) != 0;
+    if (const char* e = getenv("MRD_DEBUG_RING")) g_debug_ring = atoi(e);
+}
 
 constexpr int kBlockM = 128;
 constexpr int kNumThreads = 352;  // TMA warp + MMA warp + 8 epilogue warps + residual-loader warp
@@ -86,6 +98,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 // columns.  A sub-tile is a latency chain (TMEM load -> residual -> activation -> pack -> proxy fence -> barrier ->
 // TMA store, ~1500 cycles measured on the chained bottleneck kernel of conv_chain.cu): with one sub-tile in flight
 // per CTA that chain bounds every launch whose main loop is shorter than it.
+// Stem patch geometry (MODE_STEM): a tile is 8 output pixels x 16 output rows; its raw input patch is 37 rows x 24
+// pixels x 4 channels bf16 of the padded image.
+constexpr int kStemRow = 192;    // bytes per patch row (24 pixels x 8 B)
+constexpr int kStemRows = 37;
+
 template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -138,7 +155,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             mbar_init(rfull_bar(s), 1);
-            mbar_init(rempty_bar(s), EPI2 ? 4 : 8);  // one arrival per epilogue warp that consumed the sub-tile
+            // ONE arrival per consumed sub-tile, made by the thread that issues the sub-tile's TMA store, i.e. after
+            // every consumer thread has turned the residual into shared-memory stores behind a barrier.  An arrival
+            // per warp right after the ld.shared instructions released the slot while loads were still in flight
+            // (nothing orders an mbarrier arrive behind earlier ld.shared of the warp): under load the loader's next
+            // TMA write overtook them - a few rows of a 16-byte chunk took the residual of sub-tile q + RING
+            // (tools/stress_patterns.py, r02).
+            mbar_init(rempty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -245,12 +268,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     if (++sa == STAGES) { sa = 0; pa ^= 1u; }
                 }
             } else {
+                // the raw input patch of the tile, fetched ONCE (7 KB): the MMA reads its im2col rows straight out of
+                // it through an overlapping un-swizzled descriptor (see the issuer).  An im2col matrix fetched
+                // through an overlapping-window tensor map instead moved 57 KB per tile across the SM<->L2 fabric.
                 mbar_wait(empty_bar(sa), pa ^ 1u);
                 if (lane == 0) {
-                    mbar_expect_tx(full_bar(sa), 7u * a_box_bytes);
-                    for (int tap = 0; tap < 7; ++tap)
-                        tma_load_5d(&p.a_map[0], full_bar(sa), a_smem + sa * a_stage_bytes + tap * C::A_STAGE,
-                                    0, t.w0, t.h0, tap, t.n0);
+                    mbar_expect_tx(full_bar(sa), static_cast<uint32_t>(kStemRows * kStemRow));
+                    tma_load_3d(&p.a_map[0], full_bar(sa), a_smem + sa * a_stage_bytes, 8 * t.w0, 2 * t.h0, t.n0);
                 }
                 __syncwarp();
                 if (++sa == STAGES) { sa = 0; pa ^= 1u; }
@@ -296,13 +320,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 tc_fence_after();
                 if (lane == 0) {
 #pragma unroll
+                    // GEMM row m = (output row m / 8, output pixel m % 8) of the 8 x 16 tile; its K = 32 slice for tap
+                    // row r is 8 pixels x 4 channels = 64 contiguous bytes at pixel 2*(m % 8) of patch row
+                    // 2*(m / 8) + r.  In the un-swizzled K-major layout a core matrix is 8 rows 16 bytes apart, K
+                    // chunks are LBO apart and 8-row groups SBO apart: LBO = 16 B (chunk c of row m IS chunk 0 of
+                    // row m + c: the windows overlap) and SBO = 2 patch rows describe exactly that matrix, so no
+                    // im2col copy exists anywhere (tools/exp_hankel_desc.cu verifies the addressing).
                     for (int tap = 0; tap < 7; ++tap) {
-                        const uint64_t adesc = make_smem_desc(a_smem + sa * a_stage_bytes + tap * C::A_STAGE,
-                                                              0, C::SBO, C::LAYOUT);
                         const uint64_t bdesc = make_smem_desc(b_smem + tap * C::B_STAGE, 0, C::SBO, C::LAYOUT);
 #pragma unroll
-                        for (int k = 0; k < C::BLOCK_K / 16; ++k)
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < C::BLOCK_K / 16; ++k) {
+                            const uint64_t adesc = make_smem_desc(
+                                a_smem + sa * a_stage_bytes + tap * kStemRow + k * 32, 16, 2 * kStemRow, 0);
+                            umma_bf16(d_tmem, adesc, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(sa));
                     umma_commit(tfull_bar(acc));
@@ -457,8 +488,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
                     f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rempty_bar(rslot));
             }
             if (p.act == ACT_RELU) {
 #pragma unroll
@@ -491,8 +520,53 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 o.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
                 *reinterpret_cast<uint4*>(st_row + ((c ^ (row & 7)) << 4)) = o;
             }
+            if constexpr (STEM) {
+                if (p.pool_out) {
+                    // ---- fused MaxPool2d(3, 2, 1): the tile (8 x 16 stem pixels, rows of 64 channels) is in this
+                    // group's staging buffer.  Pooled pixel (pr, pc) of the 9 x 5 it touches takes the maximum over
+                    // the part of its 3 x 3 window that lies inside the tile; neighbouring tiles add theirs with the
+                    // same reduction.  One item = one pooled pixel x 8 channels (16 bytes).
+                    named_bar_sync(bar_a, 128);
+                    const uint8_t* tile = st_gen + grp * kStageBufBytes;
+                    const int gt = threadIdx.x - 64 - grp * 128;   // 0..127 inside the group
+                    for (int item = gt; item < 45 * 8; item += 128) {
+                        const int ch = item & 7, pp = item >> 3;
+                        const int pr = pp / 5, pc = pp - pr * 5;
+                        const int ph = (t.h0 >> 1) + pr, pw = (t.w0 >> 1) + pc;
+                        if (ph >= p.pool_h || pw >= p.pool_w) continue;
+                        __nv_bfloat162 m0 = __floats2bfloat162_rn(0.f, 0.f), m1 = m0, m2 = m0, m3 = m0;
+#pragma unroll
+                        for (int dr = -1; dr <= 1; ++dr) {
+                            const int hr = 2 * pr + dr;
+                            if (hr < 0 || hr > 15) continue;
+#pragma unroll
+                            for (int dc = -1; dc <= 1; ++dc) {
+                                const int wc = 2 * pc + dc;
+                                if (wc < 0 || wc > 7) continue;
+                                const int m = hr * 8 + wc;
+                                const uint4 v = *reinterpret_cast<const uint4*>(tile + m * 128 + ((ch ^ (m & 7)) << 4));
+                                m0 = __hmax2(m0, *reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                                m1 = __hmax2(m1, *reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                                m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&v.z));
+                                m3 = __hmax2(m3, *reinterpret_cast<const __nv_bfloat162*>(&v.w));
+                            }
+                        }
+                        uint4 o;
+                        o.x = *reinterpret_cast<uint32_t*>(&m0);
+                        o.y = *reinterpret_cast<uint32_t*>(&m1);
+                        o.z = *reinterpret_cast<uint32_t*>(&m2);
+                        o.w = *reinterpret_cast<uint32_t*>(&m3);
+                        __nv_bfloat16* dst = p.pool_out +
+                            ((static_cast<long long>(t.n0) * p.pool_h + ph) * p.pool_w + pw) * 64 + ch * 8;
+                        red_max_bf16x8(dst, o);
+                    }
+                    continue;   // the next write of this staging buffer is behind the bar_b barrier of the next tile
+                }
+            }
             fence_proxy_async_smem();
             named_bar_sync(bar_a, 128);
+            // every thread of the group has stored values that depend on its residual loads: the ring slot is free
+            if (leader && has_res) mbar_arrive(rempty_bar(q % RING));
             if (leader && p.store_bf16) {
                 if (p.c_blocked)
                     tma_store_4d(&p.c_map, st_smem + grp * kStageBufBytes, 0, t.w0, t.n_idx * NSUB + sub, 0);
@@ -564,9 +638,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
                     f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rempty_bar(rslot));
-                if (++rslot == RING) { rslot = 0; rphase ^= 1u; }
             }
             if (p.act == ACT_RELU) {
 #pragma unroll
@@ -612,6 +683,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             fence_proxy_async_smem();
             named_bar_sync(1, kEpiThreads);
+            if (has_res) {
+                // every epilogue thread has stored values that depend on its residual loads: the ring slot is free
+                if (epi_tid == 0) mbar_arrive(rempty_bar(rslot));
+                if (++rslot == RING) { rslot = 0; rphase ^= 1u; }
+            }
             if (epi_tid == 0 && p.store_bf16) {
                 if (p.c_blocked)
                     tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, 0, t.w0, t.n_idx * NSUB + sub, 0);
@@ -703,6 +779,8 @@ void pick_pipeline(ConvGemmParams* p, int block_n, bool stem) {
         int extra = (avail - r * kStageBufBytes) / stage;  // leftover smem back to the operand pipeline
         if (extra > s) s = extra > kMaxStages ? kMaxStages : extra;
     }
+    apply_debug_env();
+    if (g_debug_ring > 0 && g_debug_ring < r) r = g_debug_ring;
     p->stages = s;
     p->ring = r;
 }
@@ -1196,20 +1274,23 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
     p.store_bf16 = 1;
     g->flops = 2.0 * N * Ho * Wo * 64.0 * 147.0;
     g->bytes = 2.0 * (1.0 * N * (H + 6) * (W + 8) * 4 + 64.0 * 7 * 32 + 1.0 * N * Ho * Wo * 64);
-    p.tw = Wo >= 16 ? 16 : Wo;
-    p.th = 128 / p.tw;
-    if (p.th > Ho) p.th = Ho;
+    if (Wo % 8 != 0 || Ho % 16 != 0) {
+        set_last_error("plan_stem: output %dx%d must be a multiple of the 8 x 16 tile", Wo, Ho);
+        return -1;
+    }
+    p.tw = 8;
+    p.th = 16;
     p.nb = 1;
-    p.tiles_w = (Wo + p.tw - 1) / p.tw;
-    p.tiles_h = (Ho + p.th - 1) / p.th;
+    p.tiles_w = Wo / 8;
+    p.tiles_h = Ho / 16;
     p.tiles_img = N;
     {
-        // (k: 8 pixels x 4 channels = 32 contiguous bf16 starting at padded column 2*wo,
-        //  wo: stride 2 pixels = 16 B (windows overlap), ho: stride 2 padded rows, r: 1 padded row, n)
-        uint64_t dims[5] = {32, (uint64_t)Wo, (uint64_t)Ho, 7, (uint64_t)N};
-        uint64_t str[4] = {16, (uint64_t)2 * Wp * 8, (uint64_t)Wp * 8, (uint64_t)Hp * Wp * 8};
-        uint32_t box[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, 1, 1};
-        int rc = encode_tensor_map(&p.a_map[0], Xpad, 2, 5, dims, str, box, 64);
+        // the padded image as rows of (W+8)*4 bf16; one box = the raw patch of an 8 x 16 output tile: 37 rows
+        // (2*15 + 7 taps) x 24 pixels (2*7 + 7 taps, rounded up to a 16-byte multiple), un-swizzled
+        uint64_t dims[3] = {(uint64_t)Wp * 4, (uint64_t)Hp, (uint64_t)N};
+        uint64_t str[2] = {(uint64_t)Wp * 8, (uint64_t)Hp * Wp * 8};
+        uint32_t box[3] = {kStemRow / 2, kStemRows, 1};
+        int rc = encode_tensor_map(&p.a_map[0], Xpad, 2, 3, dims, str, box, 0);
         if (rc) return rc;
         for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
     }
@@ -1228,21 +1309,32 @@ int plan_stem(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
         if (rc) return rc;
         p.r_map = p.c_map;
     }
-    // weights-resident: 7 tap-row boxes (8 KB slots) per A stage, the 7 x 4 KB weight tiles resident
-    p.a_stage_bytes = 7 * 128 * 64;
+    // weights-resident: one raw patch (7 KB) per A stage, the 7 x 4 KB weight tiles resident
+    p.a_stage_bytes = 7168;
     p.b_res_bytes = 7 * 64 * 64;
     p.ring = 0;
-    {
-        const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
-        int st = (kSmemLimit - fixed - p.b_res_bytes) / p.a_stage_bytes;
-        p.stages = st > kMaxStages ? kMaxStages : st;
-    }
+    p.stages = kMaxStages;
     return finish_plan(g, 64);
 }
 
+int plan_stem_pool(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, int W,
+                   const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* P) {
+    // the C map is never used (nothing is stored through it): any valid tensor of the output's shape class will do
+    int rc = plan_stem(g, Xpad, N, H, W, Wst, bias, P, ACT_RELU);
+    if (rc) return rc;
+    g->p.pool_out = P;
+    g->p.pool_h = H / 4;
+    g->p.pool_w = W / 4;
+    g->p.store_bf16 = 0;
+    g->bytes = 2.0 * (1.0 * N * (H + 6) * (W + 8) * 4 + 64.0 * 7 * 32 + 1.0 * N * (H / 4) * (W / 4) * 64);
+    return 0;
+}
+
 int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
+    apply_debug_env();
     if (g->stem) {
-        if (g_split_epilogue & 4) return launch_variant<64, MODE_STEM, false, true>(g, stream, sm_limit);
+        // the fused pooling lives in the two-group epilogue
+        if ((g_split_epilogue & 4) || g->p.pool_out) return launch_variant<64, MODE_STEM, false, true>(g, stream, sm_limit);
         return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
     }
     if (g->flat3 && (g_split_epilogue & 2)) {
@@ -1266,7 +1358,12 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
             case 256: return launch_variant<256, MODE_GENERIC, true>(g, stream, sm_limit);
         }
     }
-    if (g_split_epilogue & 1) {
+    // Two-group epilogue where the per-sub-tile latency chain bounds the launch (measured, r02: GELU epilogue -5 %,
+    // short-K residual convolutions -7..-12 %); long-K GEMMs without activation are main-loop-bound and keep the
+    // single-group epilogue with its two shared staging buffers (QKV lost 5 % with the split).
+    const bool chain_bound = g->p.act == ACT_GELU || g->p.num_taps * g->p.kc_per_tap <= 6 ||
+                             (g->p.kc_split && g->p.num_k_total <= 6);
+    if ((g_split_epilogue & 1) && chain_bound && !(g->p.kc_split && g->p.num_k_total > 6)) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_GENERIC, false, true>(g, stream, sm_limit);
             case 128: return launch_variant<128, MODE_GENERIC, false, true>(g, stream, sm_limit);

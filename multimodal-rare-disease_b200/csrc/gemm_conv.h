@@ -58,6 +58,12 @@ struct alignas(64) ConvGemmParams {
     // kc_per_tap chunks.  num_k_total = total K chunks in that mode.
     int kc_split;
     int num_k_total;
+    // stem only: fused MaxPool2d(3, 2, 1) (TV:models/resnet.py:200,271).  When pool_out is set the epilogue does not
+    // store the stem tile; it pools it in shared memory and folds the partial maxima into pool_out
+    // [N, pool_h, pool_w, 64] bf16 with red.global.max (pool_out must be ZERO before the launch: post-ReLU values are
+    // >= 0, so 0 is the identity of the max and doubles as the padding value).
+    __nv_bfloat16* pool_out;
+    int pool_h, pool_w;
 };
 
 struct GemmLaunch {
@@ -108,6 +114,10 @@ int plan_conv3x3_flat(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, 
 // Wst: [64][7][32] bf16 (tap row r, then 8 pixels x 4 channels; BN folded), Y: [N,H/2,W/2,64].
 int plan_stem(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W,
               const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* Y, int act);
+// The stem with the 3x3 / stride-2 / pad-1 max pooling fused into its epilogue: P [N,H/4,W/4,64] bf16 must be zeroed
+// before every launch; the 112 x 112 stem output itself is never written.  act must be ReLU.
+int plan_stem_pool(GemmLaunch* out, const __nv_bfloat16* Xpad, int N, int H, int W,
+                   const __nv_bfloat16* Wst, const float* bias, __nv_bfloat16* P);
 
 // Weight-gradient GEMM: out_f32[M,N] += A[M,K] * W[N,K]^T with fp32 accumulation across split-K work
 // items (wide 128x256 tiles for operand reuse, K cut so that every SM gets a work item).  out_f32 must be

@@ -144,6 +144,13 @@ __device__ __forceinline__ void tma_store_4d_hint(const void* map, uint32_t src,
         : "memory");
 }
 
+// 8 bf16 maxima folded into global memory in one reduction (REDG.E.MAX.BF16x8)
+__device__ __forceinline__ void red_max_bf16x8(void* gptr, uint4 v) {
+    asm volatile("red.global.v4.bf16x2.max.noftz [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
 // L2 prefetch of a tensor box (no shared-memory destination, no barrier): used by producers that
 // hold only a few large stages to pull the tiles they will need next from HBM into L2.
 __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {

@@ -77,7 +77,8 @@ def test_training_mode_never_falls_back(model):
                   torch.ones(1, 8, dtype=torch.long))
         with pytest.raises(NotImplementedError, match="eval"):
             model.cnn_encoder(torch.zeros(1, 3, 224, 224))
-        with pytest.raises(NotImplementedError, match="inference-path"):
+        # return_embeddings is served by the training step too (same CUDA-only rule)
+        with pytest.raises(mrd_b200.MrdError, match="CUDA"):
             model(torch.zeros(1, 3, 224, 224), torch.zeros(1, 8, dtype=torch.long),
                   torch.ones(1, 8, dtype=torch.long), return_embeddings=True)
     finally:

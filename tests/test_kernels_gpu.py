@@ -280,6 +280,13 @@ def test_stem(lib, cuda, N, H, W):
     ref = F.relu(F.conv2d(x.to(BF).float(), wst.view(64, 7, 8, 4)[:, :, :7, :3].permute(0, 3, 1, 2).float(),
                           bias, stride=2, padding=3))
     _close(y.permute(0, 3, 1, 2), ref, what="stem")
+    # the same launch with MaxPool2d(3, 2, 1) fused into the epilogue: bit-equal to pooling the stored stem output
+    pooled = torch.zeros(N, H // 4, W // 4, 64, device=cuda, dtype=BF)
+    _check(lib, lib.mrd_stem_pool_bf16(xpad.data_ptr(), N, H, W, wst.data_ptr(), bias.data_ptr(), pooled.data_ptr(),
+                                       _stream()))
+    torch.cuda.synchronize()
+    want = F.max_pool2d(y.permute(0, 3, 1, 2).float(), 3, 2, 1)
+    assert torch.equal(pooled.permute(0, 3, 1, 2).float(), want), "fused stem + maxpool differs from pooling the stem"
 
 
 # ------------------------------------------------------------------ pooling

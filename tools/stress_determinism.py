@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Run-to-run determinism of the forward under every fusion switch: the same 1024-sample batch is pushed through the
+model `reps` times per configuration and the logits digests are compared (the forward has no atomics whose result
+depends on order - red.max is order-independent - so any difference is a synchronisation bug).
+
+    python tools/stress_determinism.py [reps] [batch]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import mrd_b200  # noqa: E402,F401
+from importlib import import_module  # noqa: E402
+
+synth = import_module("multimodal-rare-disease_b200.synthetic")
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+dev = torch.device("cuda:0")
+images, ids, mask = (t.to(dev) for t in synth.make_global_rows(0, batch))
+configs = {
+    "all off": {"split_epilogue": 0, "fuse_chain": 0, "fuse_pool": 0, "fuse_ds": 0},
+    "ds": {"split_epilogue": 0, "fuse_chain": 0, "fuse_pool": 0, "fuse_ds": 1},
+    "ds+epi2(generic)": {"split_epilogue": 1, "fuse_chain": 0, "fuse_pool": 0, "fuse_ds": 1},
+    "ds+epi2(generic,flat3)": {"split_epilogue": 3, "fuse_chain": 0, "fuse_pool": 0, "fuse_ds": 1},
+    "ds+epi2(all)": {"split_epilogue": 7, "fuse_chain": 0, "fuse_pool": 0, "fuse_ds": 1},
+    "ds+chain": {"split_epilogue": 0, "fuse_chain": 1, "fuse_pool": 0, "fuse_ds": 1},
+    "ds+pool": {"split_epilogue": 0, "fuse_chain": 0, "fuse_pool": 1, "fuse_ds": 1},
+    "default": {"split_epilogue": 3, "fuse_chain": 1, "fuse_pool": 1, "fuse_ds": 1},
+}
+bad = 0
+ref_digest = None
+for name, opts in configs.items():
+    model = synth.build_model(0).to(dev)
+    eng = model._engine()
+    for k, v in opts.items():
+        eng.set_option(k, float(v))
+    digests = {}
+    first = None
+    for r in range(reps):
+        with torch.no_grad():
+            out = model(images, ids, mask)["logits"].clone()
+        torch.cuda.synchronize()
+        d = synth.tensor_digest(out)[:12]
+        digests[d] = digests.get(d, 0) + 1
+        if first is None:
+            first = out
+        elif d != synth.tensor_digest(first)[:12]:
+            diff = (out - first).abs()
+            rows = (diff.max(dim=1).values > 0).nonzero().flatten().tolist()
+            print(f"   rep {r}: {len(rows)} rows differ (first {rows[:8]}), max |diff| {diff.max().item():.3e}")
+    ok = len(digests) == 1
+    bad += 0 if ok else 1
+    print(f"{name:28s} {'OK  ' if ok else 'FAIL'} {digests}", flush=True)
+print("deterministic" if bad == 0 else f"{bad} configuration(s) NOT deterministic")
+sys.exit(1 if bad else 0)
