@@ -100,6 +100,14 @@ int mrd_fusion_fwd(mrd_ctx* ctx, const float* img_emb, const float* txt_emb, int
  * x f32 [B,Din] -> logits f32 [B,C], probs f32 [B,C] (probs optional). */
 int mrd_head_fwd(mrd_ctx* ctx, const float* x, int B, float* logits, float* probs, void* stream);
 
+/* The batch-level tail of MultimodalClassifier.forward as ONE launch (tail_fused_kernel): AttentionFusion
+ * (src/fusion_model.py:245-291) -> ClassificationHead -> softmax (src/multimodal_classifier.py:73-83,166-167).
+ * img_emb f32 [B,Di], txt_emb f32 [B,Dt] -> logits f32 [B,C]; probs f32 [B,C] and fused f32 [B,Hd] optional.
+ * Falls back to the per-layer launches of mrd_fusion_fwd + mrd_head_fwd when the shapes are outside the fused
+ * kernel's range or the option "fuse_tail" is 0. */
+int mrd_fusion_head_fwd(mrd_ctx* ctx, const float* img_emb, const float* txt_emb, int B, float* fused,
+                        float* logits, float* probs, void* stream);
+
 /* MultimodalClassifier.forward (src/multimodal_classifier.py:131-177).  Outputs other than logits
  * are optional (NULL to skip): probs [B,C], img_emb [B,512], txt_emb [B,768], fused [B,512],
  * attn_i2t / attn_t2i [B,heads,1,1]. */

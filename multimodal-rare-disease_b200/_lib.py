@@ -39,6 +39,7 @@ SIGNATURES = {
     "mrd_text_encoder_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mrd_fusion_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mrd_head_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "mrd_fusion_head_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mrd_multimodal_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp]),
     "mrd_ctx_profile": (_i, [_vp, _i]),

@@ -29,6 +29,7 @@
 #include "fp32_check.h"
 #include "gemm_conv.h"
 #include "simt_gemm.h"
+#include "tail_fused.h"
 #include "tma_host.h"
 #include "train_kernels.h"
 
@@ -110,6 +111,8 @@ struct BatchPlan {
     GemmLaunch proj1, proj2;
     GemmLaunch ip, tp, i2t, t2i, f1, f2;
     std::vector<GemmLaunch> head;
+    bool has_tail = false;   // fusion + head + softmax as ONE launch (tail_fused.h); the launches above stay planned
+    TailLaunch tail;         // for the module-level entry points and as the A/B reference (option "fuse_tail")
 };
 
 }  // namespace
@@ -154,6 +157,7 @@ struct mrd_ctx {
     int head_act = MRD_ACT_RELU;
     int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
     int fuse_pool = 1;     // MaxPool2d(3,2,1) fused into the stem's epilogue (plan_stem_pool)
+    int fuse_tail = 1;     // AttentionFusion + ClassificationHead + softmax in one launch (tail_fused_kernel)
     int fuse_chain = 1;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
     // tensors; `raw` keeps the name table of the last load_weights (the host keeps the tensors alive)
@@ -195,6 +199,9 @@ struct mrd_ctx {
     float *ln_i_g = nullptr, *ln_i_b = nullptr, *ln_t_g = nullptr, *ln_t_b = nullptr;
     int fusion_dim = 512, fusion_img_in = 512, fusion_txt_in = 768;
 
+    bf16* tail_wbig = nullptr;        // [2F][img_in + txt_in]: both LayerNorm inputs straight from the embeddings
+    float *tail_bbig = nullptr, *tail_scratch = nullptr;
+    int tail_residual = -1;           // fusion_residual the packed tail weights were built with
     std::vector<LinearW> head_hidden;
     float *head_out_w = nullptr, *head_out_b = nullptr;
     int head_in = 0, head_last = 0, num_classes = 0;
@@ -525,6 +532,31 @@ int load_fusion(mrd_ctx* c, const Table& t, cudaStream_t s) {
     if (c->fusion_dim != 256 && c->fusion_dim != 512) {
         set_last_error("load_weights: fusion hidden_dim %d unsupported (256 or 512)", c->fusion_dim);
         return -2;
+    }
+    {
+        // operands of the fused tail (tail_fused.h): K-concatenated pre-LayerNorm weights from the raw parameters
+        const Tensor *wip, *bip, *wtp, *btp;
+        MRD_TRY(t.need(f + "image_proj.weight", &wip));
+        MRD_TRY(t.need(f + "image_proj.bias", &bip));
+        MRD_TRY(t.need(f + "text_proj.weight", &wtp));
+        MRD_TRY(t.need(f + "text_proj.bias", &btp));
+        CrossRaw cr[2];
+        const char* names[2] = {"image_to_text_attention.", "text_to_image_attention."};
+        for (int i = 0; i < 2; ++i) {
+            const Tensor *wv, *bv, *wo, *bo;
+            MRD_TRY(t.need(f + names[i] + "value_proj.weight", &wv));
+            MRD_TRY(t.need(f + names[i] + "value_proj.bias", &bv));
+            MRD_TRY(t.need(f + names[i] + "output_proj.weight", &wo));
+            MRD_TRY(t.need(f + names[i] + "output_proj.bias", &bo));
+            cr[i] = CrossRaw{wv->p, bv->p, wo->p, bo->p};
+        }
+        const int F = c->fusion_dim, Ii = c->fusion_img_in, Ti = c->fusion_txt_in;
+        MRD_TRY(walloc(c, &c->tail_wbig, 2LL * F * (Ii + Ti)));
+        MRD_TRY(walloc(c, &c->tail_bbig, 2LL * F));
+        MRD_TRY(walloc(c, &c->tail_scratch, 2LL * F * F + 2LL * F));
+        MRD_TRY(pack_tail_big(wip->p, bip->p, wtp->p, btp->p, cr[0], cr[1], F, Ii, Ti, c->fusion_residual,
+                              c->tail_scratch, c->tail_wbig, c->tail_bbig, s));
+        c->tail_residual = c->fusion_residual;
     }
     c->has_fusion = true;
     return 0;
@@ -892,6 +924,35 @@ int get_batch_plan(mrd_ctx* c, int B, BatchPlan** out) {
             ld = L.out;
         }
         p.has_head = true;
+    }
+    if (c->has_fusion && c->has_head && c->fuse_tail && c->tail_residual == c->fusion_residual &&
+        c->fusion_dim == c->head_in && !c->head_hidden.empty() &&
+        c->head_hidden.size() <= 3) {
+        TailWeights w = {};
+        w.w_big = c->tail_wbig; w.b_big = c->tail_bbig;
+        w.ln_i_g = c->ln_i_g; w.ln_i_b = c->ln_i_b; w.ln_t_g = c->ln_t_g; w.ln_t_b = c->ln_t_b;
+        w.w1 = c->f_1.w; w.b1 = c->f_1.b; w.w2 = c->f_2.w; w.b2 = c->f_2.b;
+        w.num_hidden = static_cast<int>(c->head_hidden.size());
+        for (int j = 0; j < w.num_hidden; ++j) {
+            w.wh[j] = c->head_hidden[j].w;
+            w.bh[j] = c->head_hidden[j].b;
+            w.hdim[j] = c->head_hidden[j].out;
+        }
+        w.head_act = c->head_act;
+        w.out_w = c->head_out_w; w.out_b = c->head_out_b;
+        w.F = c->fusion_dim; w.img_in = c->fusion_img_in; w.txt_in = c->fusion_txt_in; w.C = c->num_classes;
+        w.ln_eps = c->fusion_ln_eps;
+        bool chain = c->f_1.in == 2 * w.F && c->f_1.out == w.F && c->f_2.in == w.F && c->f_2.out == w.F;
+        int in_dim = w.F;
+        for (int j = 0; j < w.num_hidden; ++j) {
+            chain = chain && c->head_hidden[j].in == in_dim;
+            in_dim = w.hdim[j];
+        }
+        chain = chain && in_dim == c->head_last;
+        if (chain && tail_supported(w.F, w.img_in, w.txt_in, w.num_hidden, w.hdim, w.C)) {
+            MRD_TRY(plan_tail(&p.tail, w, c->b_img, c->b_txt, B));
+            p.has_tail = true;
+        }
     }
     auto ins = c->batch_plans.emplace(B, std::move(p));
     *out = &ins.first->second;
@@ -1285,6 +1346,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
+    else if (k == "fuse_tail") { c->fuse_tail = v != 0.0; c->batch_plans.clear(); }
     else if (k == "fuse_pool") { c->fuse_pool = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }
     else if (k == "split_epilogue") gemm_set_split_epilogue(static_cast<int>(v));   // process-wide A/B switch
@@ -1410,6 +1472,59 @@ int mrd_fusion_fwd(mrd_ctx* c, const float* img_emb, const float* txt_emb, int B
     return run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s);
 }
 
+namespace {
+// fusion -> head -> softmax from the bf16 embeddings in b_img / b_txt: one launch when the plan has the fused tail
+int run_tail(mrd_ctx* c, BatchPlan* bp, int B, float* fused, float* attn_i2t, float* attn_t2i, float* logits,
+             float* probs, cudaStream_t s) {
+    if (!bp->has_tail) {
+        MRD_TRY(run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s));
+        return run_head(c, bp, B, logits, probs, s);
+    }
+    {
+        ProfScope ps(c, s, "fusion+head (one launch)", CAT_TENSOR, bp->tail.flops, bp->tail.bytes);
+        MRD_TRY(launch_tail(&bp->tail, logits, probs, fused, c->fusion_dim, s));
+    }
+    // softmax over a single key: the weights are exactly 1 (src/fusion_model.py:138-164)
+    for (float* a : {attn_i2t, attn_t2i})
+        if (a) {
+            ProfScope ps(c, s, "fill_ones", CAT_MEM, 0, 4.0 * B * c->fusion_heads);
+            MRD_TRY(fill_f32(a, 1LL * B * c->fusion_heads, 1.0f, s));
+        }
+    return 0;
+}
+}  // namespace
+
+int mrd_fusion_head_fwd(mrd_ctx* c, const float* img_emb, const float* txt_emb, int B, float* fused, float* logits,
+                        float* probs, void* stream) {
+    MRD_TRY(check_ctx(c));
+    if (B <= 0) return 0;
+    if (!c->has_fusion || !c->has_head) {
+        set_last_error("mrd_fusion_head_fwd needs fusion and classifier weights");
+        return -3;
+    }
+    if (c->fp32_check) {
+        set_last_error("mrd_fusion_head_fwd has no fp32 check mode: call mrd_fusion_fwd and mrd_head_fwd");
+        return -1;
+    }
+    if (c->fusion_dim != c->head_in) {
+        set_last_error("fusion / head dimensions do not chain (%d->%d)", c->fusion_dim, c->head_in);
+        return -1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MRD_TRY(ensure_batch_ws(c, B));
+    BatchPlan* bp;
+    MRD_TRY(get_batch_plan(c, B, &bp));
+    {
+        ProfScope ps(c, s, "cast_f32_to_bf16", CAT_MEM, 0, 6.0 * B * c->fusion_img_in);
+        MRD_TRY(cast_f32_to_bf16(img_emb, c->fusion_img_in, B, c->fusion_img_in, c->b_img, c->fusion_img_in, s));
+    }
+    {
+        ProfScope ps(c, s, "cast_f32_to_bf16", CAT_MEM, 0, 6.0 * B * c->fusion_txt_in);
+        MRD_TRY(cast_f32_to_bf16(txt_emb, c->fusion_txt_in, B, c->fusion_txt_in, c->b_txt, c->fusion_txt_in, s));
+    }
+    return run_tail(c, bp, B, fused, nullptr, nullptr, logits, probs, s);
+}
+
 int mrd_head_fwd(mrd_ctx* c, const float* x, int B, float* logits, float* probs, void* stream) {
     MRD_TRY(check_ctx(c));
     if (B <= 0) return 0;
@@ -1479,8 +1594,7 @@ int mrd_multimodal_fwd(mrd_ctx* c, const void* images, int img_dtype, const long
     MRD_TRY(run_backbone(c, images, img_dtype, B, H, W, nullptr, nullptr, s));
     MRD_TRY(run_projection(c, bp, img_emb, s));
     MRD_TRY(run_bert(c, ids, mask, mask_dtype, B, S, txt_emb, nullptr, nullptr, s));
-    MRD_TRY(run_fusion(c, bp, B, fused, attn_i2t, attn_t2i, s));
-    return run_head(c, bp, B, logits, probs, s);
+    return run_tail(c, bp, B, fused, attn_i2t, attn_t2i, logits, probs, s);
 }
 
 int mrd_ctx_profile(mrd_ctx* c, int enable) {

@@ -252,6 +252,22 @@ class Engine:
                                                    _stream(self.device)), "mrd_fusion_fwd")
         return fused, a1, a2
 
+    def fusion_head(self, img_emb, txt_emb, hidden_dim: int, num_classes: int, want_fused=False):
+        """AttentionFusion -> ClassificationHead -> softmax as one launch (mrd_fusion_head_fwd)."""
+        if img_emb.dim() != 2 or txt_emb.dim() != 2 or img_emb.shape[0] != txt_emb.shape[0]:
+            raise ValueError("fusion_head expects [B,Di] and [B,Dt] embeddings")
+        img = img_emb.to(self.device, torch.float32).contiguous()
+        txt = txt_emb.to(self.device, torch.float32).contiguous()
+        B = img.shape[0]
+        logits, probs = self._f32(B, num_classes), self._f32(B, num_classes)
+        fused = self._f32(B, hidden_dim) if want_fused else None
+        if B:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mrd_fusion_head_fwd(self._ctx, img.data_ptr(), txt.data_ptr(), B, _ptr(fused),
+                                                        logits.data_ptr(), probs.data_ptr(),
+                                                        _stream(self.device)), "mrd_fusion_head_fwd")
+        return logits, probs, fused
+
     def head(self, x, num_classes: int, want_probs=True):
         if x.dim() != 2:
             raise ValueError("classification head expects [B,D] features")
