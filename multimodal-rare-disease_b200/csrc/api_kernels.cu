@@ -27,6 +27,22 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }
 
+int mrd_gemm_ln_bf16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias, void* C,
+                     long long ldc, const void* residual, long long ld_res, const float* gamma, const float* beta,
+                     float eps, void* stream) {
+    GemmLaunch g;
+    int rc = plan_gemm_ln(&g, static_cast<const __nv_bfloat16*>(A), lda, M, K, static_cast<const __nv_bfloat16*>(W), N,
+                          bias, static_cast<__nv_bfloat16*>(C), ldc, static_cast<const __nv_bfloat16*>(residual), ld_res,
+                          gamma, beta, eps);
+    if (rc > 0) {
+        set_last_error("mrd_gemm_ln_bf16: shape M=%d N=%d outside the fused LayerNorm kernel's range (N = 512 / 768 / "
+                       "1024, enough rows for 256-wide tiles)", M, N);
+        return -1;
+    }
+    if (rc) return rc;
+    return launch_gemm(&g, static_cast<cudaStream_t>(stream));
+}
+
 int mrd_gemm_splitk_f32(const void* A, long long lda, int M, int K, const void* W, int N, float* out_f32,
                         long long ld_f32, const int* dyn_k, void* stream) {
     GemmLaunch g;

@@ -103,7 +103,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 constexpr int kStemRow = 192;    // bytes per patch row (24 pixels x 8 B)
 constexpr int kStemRows = 37;
 
-template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false>
+// LNC: LayerNorm over the whole output row in the epilogue.  The n_tiles_n CTAs of a thread-block cluster work on
+// the same 128-row stripe (tile = blockIdx.x + i * gridDim.x with gridDim.x a multiple of n_tiles_n: the cluster
+// rank IS the column tile).  Epilogue pass 1: accumulator + bias + residual -> per-row partial (mean, M2) of this
+// CTA's columns, the fp32 sums go BACK into TMEM (tcgen05.st); the partials are written into every CTA of the cluster
+// (st.shared::cluster) and counted on an mbarrier there.  Pass 2: combine the partials (Chan), normalise the TMEM
+// values, store.  HF:models/bert/modeling_bert.py:294-298,352-356.
+constexpr int kLnStatBytes = 2 * 128 * 8 * 8;   // two buffers x 128 rows x up to 8 partials x (mean, M2)
+
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BLOCK_N, MODE>;
@@ -169,6 +177,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_init(tempty_bar(a), EPI2 ? 4 * (BLOCK_N / 64) : 8);
         }
         mbar_init(bres_bar, 1);
+        if constexpr (LNC) {   // statistics of one stripe have arrived: one arrival per epilogue warp of the cluster
+            mbar_init(bar_smem + 400u, 8u * p.n_tiles_n);
+            mbar_init(bar_smem + 408u, 8u * p.n_tiles_n);
+        }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 320);
@@ -176,6 +188,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (LNC) cluster_sync_all();   // the peers' barriers exist before anyone arrives on them
 
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
     // prefetch) overlaps the tail of the previous kernel in the stream; nothing below may touch
@@ -428,6 +441,147 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 }
             }
         }
+    } else if (LNC) {
+        // ------------------------------------------------------------ epilogue with LayerNorm across the cluster
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int epi_tid = threadIdx.x - 64;
+        const bool has_res = p.has_res != 0;
+        const int csize = p.n_tiles_n;
+        const int npart = 2 * csize;                     // partials per row: (CTA, column half)
+        const uint32_t crank = cluster_ctarank();
+        const uint32_t stats_smem = bar_smem + kBarBytes;
+        const float2* stats_gen = reinterpret_cast<const float2*>(smem_gen + (stats_smem - smem_base));
+        constexpr float kPartN = static_cast<float>(NSUB * 32);   // columns behind one partial
+        const float inv_n = 1.0f / (static_cast<float>(csize) * BLOCK_N);
+        int rslot = 0;
+        uint32_t rphase = 0;
+        int q = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1, sb = it & 1;
+            const TileCoord t = decode_tile(p, bid + it * nblk);
+            const uint32_t tbase =
+                tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * 32;
+            mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
+            tc_fence_after();
+            // ---- pass 1: x = acc + bias + residual back into TMEM, running sum / sum of squares of this thread's columns
+            float sum = 0.0f, ssq = 0.0f;
+            for (int sub = 0; sub < NSUB; ++sub) {
+                const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;
+                uint32_t v[32];
+                tmem_ld32(tbase + sub * 64, v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (has_res) {
+                    mbar_wait(rfull_bar(rslot), rphase);
+                    const uint8_t* r_row = ring_gen + rslot * kStageBufBytes + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int chunk = (half * 4 + c) ^ (row & 7);
+                        const uint4 r4 = *reinterpret_cast<const uint4*>(r_row + chunk * 16);
+                        const float2 r0 = unpack_bf16(r4.x), r1 = unpack_bf16(r4.y),
+                                     r2 = unpack_bf16(r4.z), r3 = unpack_bf16(r4.w);
+                        f[c * 8 + 0] += r0.x; f[c * 8 + 1] += r0.y;
+                        f[c * 8 + 2] += r1.x; f[c * 8 + 3] += r1.y;
+                        f[c * 8 + 4] += r2.x; f[c * 8 + 5] += r2.y;
+                        f[c * 8 + 6] += r3.x; f[c * 8 + 7] += r3.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    sum += f[j];
+                    ssq = fmaf(f[j], f[j], ssq);
+                    v[j] = __float_as_uint(f[j]);
+                }
+                tmem_st32(tbase + sub * 64, v);
+                tmem_st_wait();
+                if (has_res) {
+                    // the stores above consumed every residual load of this thread: behind the barrier the slot is free
+                    named_bar_sync(2, kEpiThreads);
+                    if (epi_tid == 0) mbar_arrive(rempty_bar(rslot));
+                    if (++rslot == RING) { rslot = 0; rphase ^= 1u; }
+                }
+            }
+            // ---- publish (mean, M2) of these kPartN columns to every CTA of the cluster
+            {
+                const float mean_p = sum * (1.0f / kPartN);
+                const float m2_p = fmaxf(ssq - sum * mean_p, 0.0f);
+                const uint32_t slot_addr =
+                    stats_smem + static_cast<uint32_t>(((sb * 128 + row) * 8 + static_cast<int>(crank) * 2 + half) * 8);
+                for (int r = 0; r < csize; ++r) st_cluster_f32x2(mapa_shared(slot_addr, r), mean_p, m2_p);
+                fence_acq_rel_cluster();
+                __syncwarp();
+                if (lane == 0)
+                    for (int r = 0; r < csize; ++r) mbar_arrive_cluster(mapa_shared(bar_smem + 400u + 8u * sb, r));
+            }
+            mbar_wait_cluster(bar_smem + 400u + 8u * sb, (it >> 1) & 1u);
+            float mean = 0.0f;
+            {
+                const float2* pr = stats_gen + (sb * 128 + row) * 8;
+                for (int i = 0; i < npart; ++i) mean += pr[i].x;
+                mean *= 1.0f / static_cast<float>(npart);
+                float m2 = 0.0f;
+                for (int i = 0; i < npart; ++i) {
+                    const float d = pr[i].x - mean;
+                    m2 += pr[i].y + kPartN * d * d;
+                }
+                sum = rsqrtf(m2 * inv_n + p.ln_eps);
+            }
+            const float rstd = sum;
+            // ---- pass 2: normalise, store
+            for (int sub = 0; sub < NSUB; ++sub, ++q) {
+                const uint32_t buf = q & 1u;
+                const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;
+                uint32_t v[32];
+                tmem_ld32(tbase + sub * 64, v);
+                tmem_ld_wait();
+                if (sub == NSUB - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col0 + j));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col0 + j));
+                    f[j + 0] = fmaf((__uint_as_float(v[j + 0]) - mean) * rstd, g4.x, b4.x);
+                    f[j + 1] = fmaf((__uint_as_float(v[j + 1]) - mean) * rstd, g4.y, b4.y);
+                    f[j + 2] = fmaf((__uint_as_float(v[j + 2]) - mean) * rstd, g4.z, b4.z);
+                    f[j + 3] = fmaf((__uint_as_float(v[j + 3]) - mean) * rstd, g4.w, b4.w);
+                }
+                if (epi_tid == 0) tma_store_wait_read<1>();
+                named_bar_sync(2, kEpiThreads);
+                uint8_t* st_row = st_gen + buf * kStageBufBytes + row * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 o;
+                    o.x = pack_bf16(f[c * 8 + 0], f[c * 8 + 1]);
+                    o.y = pack_bf16(f[c * 8 + 2], f[c * 8 + 3]);
+                    o.z = pack_bf16(f[c * 8 + 4], f[c * 8 + 5]);
+                    o.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
+                    const int chunk = (half * 4 + c) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(st_row + chunk * 16) = o;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, kEpiThreads);
+                if (epi_tid == 0) {
+                    tma_store_4d(&p.c_map, st_smem + buf * kStageBufBytes, t.n_idx * BLOCK_N + sub * 64, t.w0, t.h0,
+                                 t.n0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
     } else if (EPI2) {
         // ------------------------------------------------------------ epilogue, two groups of four warps
         const int grp = (warp - 2) >> 2;
@@ -702,17 +856,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (LNC) cluster_sync_all();   // no CTA leaves while a peer may still write its statistics buffer
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<C::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false>
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false>
 int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
-    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK, EPI2>;
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK, EPI2, LNC>;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -724,7 +879,7 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     }
     const int smem = MODE != MODE_GENERIC
                          ? C::FIXED + g->p.stages * g->p.a_stage_bytes + g->p.b_res_bytes
-                         : C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes;
+                         : C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes + (LNC ? kLnStatBytes : 0);
     cudaLaunchConfig_t cfg = {};
     int grid = g->grid;
     if (sm_limit > 0 && grid > sm_limit) {
@@ -740,13 +895,37 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     // no programmatic dependent launch under an SM cap: the early-launched CTAs of the next kernel would sit on
     // the SMs that the cap leaves to the other stream
     attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && sm_limit <= 0) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (LNC) {
+        // one cluster = the n_tiles_n column tiles of a 128-row stripe; as many clusters as are co-resident
+        const int cs = g->p.n_tiles_n;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cs;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+        static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (max_clusters[cs] == 0) {
+            cfg.gridDim = dim3(cs * 16);
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kfn, &cfg);
+            if (e != cudaSuccess || n <= 0) {
+                set_last_error("cudaOccupancyMaxActiveClusters(cluster of %d): %s", cs, cudaGetErrorString(e));
+                return e != cudaSuccess ? -static_cast<int>(e) : -1;
+            }
+            max_clusters[cs] = n;
+        }
+        int clusters = grid / cs;
+        if (clusters > max_clusters[cs]) clusters = max_clusters[cs];
+        if (clusters < 1) clusters = 1;
+        cfg.gridDim = dim3(clusters * cs);
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, g->p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -915,6 +1094,31 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
         p.r_map = p.a_map[0];  // never dereferenced (has_res == 0)
     }
     return finish_plan(g, bn);
+}
+
+int plan_gemm_ln(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* W, int N,
+                 const float* bias, __nv_bfloat16* Cout, long long ldc, const __nv_bfloat16* residual,
+                 long long ld_res, const float* gamma, const float* beta, float eps) {
+    if (N % 256 != 0 || N / 256 < 2 || N / 256 > 4 || !Cout || !bias || !gamma || !beta) return 1;
+    MRD_GEMM_TRY(plan_gemm(g, A, lda, M, K, W, N, bias, Cout, ldc, residual, ld_res, nullptr, 0, ACT_NONE));
+    if (g->block_n != 256) return 1;   // few rows: narrower tiles fill the SMs better than clusters of wide ones
+    ConvGemmParams& p = g->p;
+    p.ln_g = gamma;
+    p.ln_b = beta;
+    p.ln_eps = eps;
+    g->lnc = 1;
+    // room for the statistics buffers: three operand stages, two residual sub-tiles in flight
+    if (p.has_res) {
+        p.stages = 3;
+        p.ring = 2;
+    } else if (p.stages > 3) {
+        p.stages = 3;
+    }
+    const int cs = p.n_tiles_n;
+    g->grid = g->grid / cs * cs;
+    if (g->grid < cs) g->grid = cs;
+    g->bytes += 8.0 * N;   // gamma / beta
+    return 0;
 }
 
 int plan_gemm_splitk(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
@@ -1337,6 +1541,7 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
         if ((g_split_epilogue & 4) || g->p.pool_out) return launch_variant<64, MODE_STEM, false, true>(g, stream, sm_limit);
         return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
     }
+    if (g->lnc) return launch_variant<256, MODE_GENERIC, false, false, true>(g, stream, sm_limit);
     if (g->flat3 && (g_split_epilogue & 2)) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_FLAT3, false, true>(g, stream, sm_limit);

@@ -64,6 +64,12 @@ struct alignas(64) ConvGemmParams {
     // >= 0, so 0 is the identity of the max and doubles as the padding value).
     __nv_bfloat16* pool_out;
     int pool_h, pool_w;
+    // LayerNorm in the epilogue (plan_gemm_ln): the n_tiles_n CTAs of a thread-block cluster hold one 128-row stripe
+    // of the whole output row between them, exchange per-row partial statistics through distributed shared memory
+    // and store LayerNorm(A W^T + bias + residual) * ln_g + ln_b.
+    const float* ln_g;
+    const float* ln_b;
+    float ln_eps;
 };
 
 struct GemmLaunch {
@@ -71,6 +77,7 @@ struct GemmLaunch {
     int block_n;  // 64, 128 or 256
     int stem;     // 1: 5-D overlapping-window A map, BLOCK_K = 32
     int flat3;    // 1: flat-shift 3x3 stride-1 mode (halo span in smem, taps = row-shifted views)
+    int lnc;      // 1: LayerNorm epilogue across a cluster of n_tiles_n CTAs (plan_gemm_ln)
     int grid;
     double flops;  // algorithmic FLOPs (2*M*N*K, un-padded), for reporting
     double bytes;  // algorithmic bytes: A + W read once, C written once (+ residual read)
@@ -84,6 +91,15 @@ int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int
               const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* C, long long ldc,
               const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
               int act, int c_blocked = 0);
+
+// C = LayerNorm(A W^T + bias + residual) over the whole row (nn.LayerNorm(N), eps), gamma / beta fp32 [N]:
+// HF:models/bert/modeling_bert.py:294-298,352-356 (dense -> dropout -> LayerNorm(x + input)) as ONE launch.
+// N = c * 256 with c in [2, 4] (BERT-base: 3): a cluster of c CTAs owns a 128-row stripe.  Returns 1 (no error
+// message) when the shape cannot use it (few rows: the plain GEMM picks narrower tiles) - the caller then plans the
+// GEMM and a LayerNorm launch.
+int plan_gemm_ln(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* W, int N,
+                 const float* bias, __nv_bfloat16* C, long long ldc, const __nv_bfloat16* residual, long long ld_res,
+                 const float* gamma, const float* beta, float eps);
 
 // ksize in {1,3}, stride in {1,2}, padding = ksize/2.  X: [N,H,W,Cin] bf16, Wt: [Cout][k][k][Cin]
 // bf16 (BN already folded), Y: [N,H/stride,W/stride,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0.

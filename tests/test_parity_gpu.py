@@ -198,6 +198,37 @@ def test_fused_tail_vs_oracle(cuda, state):
     assert torch.equal(one[0], logits[77])
 
 
+def test_fused_layernorm_vs_separate_launch(cuda, state):
+    """BERT with LayerNorm in the GEMM epilogue (cluster kernel, option fuse_ln, active from ~6.4k tokens per pass)
+    against the separate LayerNorm launches and against the oracle on the first rows."""
+    model = _use(state, "sens")
+    sd = {k: v.float() for k, v in state["sens"].items() if v.is_floating_point()}
+    B, S = 96, 128
+    lengths = [S if i % 3 == 0 else 1 + (i * 37) % S for i in range(B)]
+    _, ids, mask = synth.make_inputs(B, S, 11, lengths, H=32, W=32)
+    enc = model.text_encoder
+    eng = model._engine()
+    with torch.no_grad():
+        fused = enc(ids.cuda(), mask.cuda()).cpu()
+        again = enc(ids.cuda(), mask.cuda()).cpu()
+        eng.set_option("fuse_ln", 0.0)
+        try:
+            n0 = eng.launch_count
+            separate = enc(ids.cuda(), mask.cuda()).cpu()
+            n_sep = eng.launch_count - n0
+        finally:
+            eng.set_option("fuse_ln", 1.0)
+        n0 = eng.launch_count
+        enc(ids.cuda(), mask.cuda())
+        n_fused = eng.launch_count - n0
+        ref = oracle.text_encoder(sd, ids[:8], mask[:8])
+    assert n_sep - n_fused == 22, (n_sep, n_fused)   # two LayerNorm launches less in each of the 11 full layers
+    assert torch.equal(fused, again), "fused LayerNorm must be deterministic"
+    assert _rel_rows(fused, separate) <= REL_TOL
+    assert _rel_rows(fused[:8], ref) <= REL_TOL
+    assert _rel_rows(separate[:8], ref) <= REL_TOL
+
+
 def test_unimodal_classifiers_vs_oracle(cuda, state):
     torch.manual_seed(3)
     cfg = mrd_b200.Config()
