@@ -47,7 +47,8 @@ SIGNATURES = {
     "mrd_ctx_launch_count": (_ll, [_vp]),
     "mrd_ctx_device_bytes": (_ll, [_vp]),
     "mrd_gemm_bf16": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp]),
-    "mrd_gemm_ln_bf16": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp, _vp, C.c_float, _vp]),
+    "mrd_gemm_ln_bf16": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _f, _vp, _vp]),
+    "mrd_gemm_ln_ws_bytes": (_ll, [_i]),
     "mrd_gemm_splitk_f32": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _vp, _vp]),
     "mrd_conv2d_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "mrd_conv1x1_dual_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),

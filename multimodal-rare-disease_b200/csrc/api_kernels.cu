@@ -29,11 +29,11 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
 
 int mrd_gemm_ln_bf16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias, void* C,
                      long long ldc, const void* residual, long long ld_res, const float* gamma, const float* beta,
-                     float eps, void* stream) {
+                     float eps, void* stats_ws, void* stream) {
     GemmLaunch g;
     int rc = plan_gemm_ln(&g, static_cast<const __nv_bfloat16*>(A), lda, M, K, static_cast<const __nv_bfloat16*>(W), N,
                           bias, static_cast<__nv_bfloat16*>(C), ldc, static_cast<const __nv_bfloat16*>(residual), ld_res,
-                          gamma, beta, eps);
+                          gamma, beta, eps, stats_ws);
     if (rc > 0) {
         set_last_error("mrd_gemm_ln_bf16: shape M=%d N=%d outside the fused LayerNorm kernel's range (N = 512 / 768 / "
                        "1024, enough rows for 256-wide tiles)", M, N);
@@ -42,6 +42,8 @@ int mrd_gemm_ln_bf16(const void* A, long long lda, int M, int K, const void* W, 
     if (rc) return rc;
     return launch_gemm(&g, static_cast<cudaStream_t>(stream));
 }
+
+long long mrd_gemm_ln_ws_bytes(int M) { return static_cast<long long>(gemm_ln_ws_bytes(M)); }
 
 int mrd_gemm_splitk_f32(const void* A, long long lda, int M, int K, const void* W, int N, float* out_f32,
                         long long ld_f32, const int* dyn_k, void* stream) {

@@ -98,8 +98,8 @@ struct TextPlan {
     int blocked_qkv = 0;  // QKV written as [36][T][64] for the tcgen05 attention (S <= 128)
     struct LayerPlan {
         GemmLaunch qkv, o, f1, f2;
-        GemmLaunch o_ln, f2_ln;   // dense + residual + LayerNorm in one launch (plan_gemm_ln), when ln_fused
-        bool ln_fused = false;
+        GemmLaunch o_ln, f2_ln;   // dense + residual + LayerNorm in one launch (plan_gemm_ln)
+        bool o_fused = false, f2_fused = false;
     };
     std::vector<LayerPlan> layers;
     // last layer, CLS rows only (M = B): everything after its attention feeds nothing but the CLS row
@@ -159,7 +159,10 @@ struct mrd_ctx {
     int head_act = MRD_ACT_RELU;
     int fuse_ds = 1;       // conv3 + downsample of a stage's first bottleneck as one K-concatenated GEMM
     int fuse_pool = 1;     // MaxPool2d(3,2,1) fused into the stem's epilogue (plan_stem_pool)
-    int fuse_ln = 1;       // BERT: LayerNorm in the epilogue of the attention-output / FFN2 GEMMs (plan_gemm_ln)
+    // BERT: LayerNorm in the epilogue of the dense + residual GEMMs (plan_gemm_ln).  1 = FFN2 only, statistics through
+    // L2 (measured, r02: the two-pass epilogue hides under the K = 3072 main loop, -25 us per launch; under the K = 768
+    // main loop of the attention output it does not: 153 vs 140 us); 2 = both GEMMs, cluster / DSMEM exchange; 0 = off
+    int fuse_ln = 1;
     int fuse_tail = 1;     // AttentionFusion + ClassificationHead + softmax in one launch (tail_fused_kernel)
     int fuse_chain = 1;    // bit (L-1): chain conv3(+ds)+add of the blocks of stage L with the next block's conv1
     // fp32 check mode (fp32_check.h): forwards run the plain-fp32 SIMT kernels on the caller's raw fp32
@@ -234,6 +237,7 @@ struct mrd_ctx {
          *t_cls_ffn = nullptr;  // CLS-row tail of the last layer
     float* t_bias = nullptr;   // key bias per packed row
     int *t_seq_off = nullptr, *t_row_tok = nullptr, *t_nrows = nullptr, *t_scratch = nullptr;
+    void* t_ln_ws = nullptr;   // statistics exchange of the LayerNorm GEMMs (gemm_ln_ws_bytes; zero between launches)
     // batch buffers
     bf16 *b_pooled = nullptr, *b_projh = nullptr, *b_img = nullptr, *b_txt = nullptr, *b_ip = nullptr,
          *b_tp = nullptr, *b_prei = nullptr, *b_pret = nullptr, *b_cat = nullptr, *b_fh = nullptr,
@@ -771,7 +775,8 @@ int ensure_text_ws(mrd_ctx* c, int tokens, int seqs) {
     const int Hd = c->hidden;
     const long long Sq = c->text_ws_seqs;  // most sequences one pass can hold
     size_t total = 4 * pad1k(T * Hd, 2) + pad1k(T * 3 * Hd, 2) + pad1k(T * c->ffn, 2) +
-                   4 * pad1k(T + 2, 4) + pad1k(1, 4) + 4 * pad1k(Sq * Hd, 2) + pad1k(Sq * c->ffn, 2);
+                   4 * pad1k(T + 2, 4) + pad1k(1, 4) + 4 * pad1k(Sq * Hd, 2) + pad1k(Sq * c->ffn, 2) +
+                   pad1k(static_cast<long long>(gemm_ln_ws_bytes(tokens)), 1);
     MRD_TRY(arena_reset(c, &c->text_ws, total));
     c->t_h = arena_take<bf16>(&c->text_ws, T * Hd);
     c->t_h2 = arena_take<bf16>(&c->text_ws, T * Hd);
@@ -789,6 +794,7 @@ int ensure_text_ws(mrd_ctx* c, int tokens, int seqs) {
     c->t_row_tok = arena_take<int>(&c->text_ws, T + 2);
     c->t_scratch = arena_take<int>(&c->text_ws, T + 2);
     c->t_nrows = arena_take<int>(&c->text_ws, 1);
+    c->t_ln_ws = arena_take<char>(&c->text_ws, static_cast<long long>(gemm_ln_ws_bytes(tokens)));
     c->text_ws_tokens = tokens;
     // rows beyond the live token count are read (never used) by tile-granular kernels: keep every
     // byte of the workspace a finite number from the start
@@ -824,19 +830,20 @@ int get_text_plan(mrd_ctx* c, int B, int S, TextPlan** out) {
         lp.qkv.p.dyn_rows = lp.o.p.dyn_rows = lp.f1.p.dyn_rows = lp.f2.p.dyn_rows = c->t_nrows;
         // dense + residual + LayerNorm as one launch (a cluster of Hd/256 CTAs per 128-token stripe): the
         // normalised rows go straight to the buffer the separate LayerNorm launch would have written
-        lp.ln_fused = false;
+        lp.o_fused = lp.f2_fused = false;
         if (c->fuse_ln) {
-            int r1 = plan_gemm_ln(&lp.o_ln, c->t_ctx, Hd, T, Hd, L.o.w, Hd, L.o.b, c->t_h2, Hd, c->t_h, Hd, L.ln1g,
-                                  L.ln1b, c->bert_ln_eps);
-            if (r1 < 0) return r1;
-            int r2 = r1 == 0 ? plan_gemm_ln(&lp.f2_ln, c->t_ffn, c->ffn, T, c->ffn, L.f2.w, Hd, L.f2.b, c->t_h, Hd,
-                                            c->t_h2, Hd, L.ln2g, L.ln2b, c->bert_ln_eps)
-                             : 1;
+            void* ws = c->fuse_ln == 1 ? c->t_ln_ws : nullptr;
+            int r2 = plan_gemm_ln(&lp.f2_ln, c->t_ffn, c->ffn, T, c->ffn, L.f2.w, Hd, L.f2.b, c->t_h, Hd, c->t_h2, Hd,
+                                  L.ln2g, L.ln2b, c->bert_ln_eps, ws);
             if (r2 < 0) return r2;
-            if (r1 == 0 && r2 == 0) {
-                lp.o_ln.p.dyn_rows = lp.f2_ln.p.dyn_rows = c->t_nrows;
-                lp.ln_fused = true;
+            lp.f2_fused = r2 == 0;
+            if (c->fuse_ln >= 2) {
+                int r1 = plan_gemm_ln(&lp.o_ln, c->t_ctx, Hd, T, Hd, L.o.w, Hd, L.o.b, c->t_h2, Hd, c->t_h, Hd,
+                                      L.ln1g, L.ln1b, c->bert_ln_eps, ws);
+                if (r1 < 0) return r1;
+                lp.o_fused = r1 == 0;
             }
+            lp.o_ln.p.dyn_rows = lp.f2_ln.p.dyn_rows = c->t_nrows;
         }
     }
     {
@@ -1200,24 +1207,22 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                 }
                 break;
             }
-            if (lp.ln_fused) {
+            if (lp.o_fused) {
                 MRD_TRY(run(c, "bert.attn_out+res+ln", lp.o_ln, s));
-                MRD_TRY(run(c, "bert.ffn1+gelu", lp.f1, s));
-                MRD_TRY(run(c, "bert.ffn2+res+ln", lp.f2_ln, s));
             } else {
                 MRD_TRY(run(c, "bert.attn_out+res", lp.o, s));
-                {
-                    ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
-                    MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b, c->bert_ln_eps, T,
-                                               Hd, c->t_h2, Hd, nullptr, 0, s, c->t_nrows));
-                }
-                MRD_TRY(run(c, "bert.ffn1+gelu", lp.f1, s));
+                ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
+                MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln1g, L.ln1b, c->bert_ln_eps, T,
+                                           Hd, c->t_h2, Hd, nullptr, 0, s, c->t_nrows));
+            }
+            MRD_TRY(run(c, "bert.ffn1+gelu", lp.f1, s));
+            if (lp.f2_fused) {
+                MRD_TRY(run(c, "bert.ffn2+res+ln", lp.f2_ln, s));
+            } else {
                 MRD_TRY(run(c, "bert.ffn2+res", lp.f2, s));
-                {
-                    ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
-                    MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
-                                               Hd, c->t_h, Hd, nullptr, 0, s, c->t_nrows));
-                }
+                ProfScope ps(c, s, "bert.layernorm", CAT_MEM, 0, ln_bytes);
+                MRD_TRY(layernorm_residual(c->t_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b, c->bert_ln_eps, T,
+                                           Hd, c->t_h, Hd, nullptr, 0, s, c->t_nrows));
             }
             MRD_TRY(export_hidden(i + 1));
         }
@@ -1371,7 +1376,7 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "head_act") { c->head_act = static_cast<int>(v); c->batch_plans.clear(); }
     else if (k == "fp32_check") c->fp32_check = v != 0.0;
     else if (k == "fuse_ds") { c->fuse_ds = v != 0.0; c->cnn_plans.clear(); }
-    else if (k == "fuse_ln") { c->fuse_ln = v != 0.0; c->text_plans.clear(); }
+    else if (k == "fuse_ln") { c->fuse_ln = static_cast<int>(v); c->text_plans.clear(); }
     else if (k == "fuse_tail") { c->fuse_tail = v != 0.0; c->batch_plans.clear(); }
     else if (k == "fuse_pool") { c->fuse_pool = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }

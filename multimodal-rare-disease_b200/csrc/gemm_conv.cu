@@ -188,7 +188,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if constexpr (LNC) cluster_sync_all();   // the peers' barriers exist before anyone arrives on them
+    if constexpr (LNC) {
+        if (!p.ln_stats) cluster_sync_all();   // the peers' barriers exist before anyone arrives on them
+    }
 
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
     // prefetch) overlaps the tail of the previous kernel in the stream; nothing below may touch
@@ -450,7 +452,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const bool has_res = p.has_res != 0;
         const int csize = p.n_tiles_n;
         const int npart = 2 * csize;                     // partials per row: (CTA, column half)
-        const uint32_t crank = cluster_ctarank();
+        const bool via_global = p.ln_stats != nullptr;
+        const uint32_t crank = via_global ? 0u : cluster_ctarank();
         const uint32_t stats_smem = bar_smem + kBarBytes;
         const float2* stats_gen = reinterpret_cast<const float2*>(smem_gen + (stats_smem - smem_base));
         constexpr float kPartN = static_cast<float>(NSUB * 32);   // columns behind one partial
@@ -511,10 +514,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                     if (++rslot == RING) { rslot = 0; rphase ^= 1u; }
                 }
             }
-            // ---- publish (mean, M2) of these kPartN columns to every CTA of the cluster
-            {
-                const float mean_p = sum * (1.0f / kPartN);
-                const float m2_p = fmaxf(ssq - sum * mean_p, 0.0f);
+            // ---- publish (mean, M2) of these kPartN columns to the CTAs that hold the rest of the row
+            const float mean_p = sum * (1.0f / kPartN);
+            const float m2_p = fmaxf(ssq - sum * mean_p, 0.0f);
+            float2 part[8];
+            if (!via_global) {
                 const uint32_t slot_addr =
                     stats_smem + static_cast<uint32_t>(((sb * 128 + row) * 8 + static_cast<int>(crank) * 2 + half) * 8);
                 for (int r = 0; r < csize; ++r) st_cluster_f32x2(mapa_shared(slot_addr, r), mean_p, m2_p);
@@ -522,21 +526,49 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 __syncwarp();
                 if (lane == 0)
                     for (int r = 0; r < csize; ++r) mbar_arrive_cluster(mapa_shared(bar_smem + 400u + 8u * sb, r));
-            }
-            mbar_wait_cluster(bar_smem + 400u + 8u * sb, (it >> 1) & 1u);
-            float mean = 0.0f;
-            {
+                mbar_wait_cluster(bar_smem + 400u + 8u * sb, (it >> 1) & 1u);
                 const float2* pr = stats_gen + (sb * 128 + row) * 8;
-                for (int i = 0; i < npart; ++i) mean += pr[i].x;
-                mean *= 1.0f / static_cast<float>(npart);
-                float m2 = 0.0f;
-                for (int i = 0; i < npart; ++i) {
-                    const float d = pr[i].x - mean;
-                    m2 += pr[i].y + kPartN * d * d;
+                for (int i = 0; i < npart; ++i) part[i] = pr[i];
+            } else {
+                // through L2: the csize CTAs of a stripe are neighbours in the persistent tile order, so all of them
+                // are resident (grid <= SM count) and a spin on the stripe's arrival counter cannot deadlock
+                const int stripe = (bid + it * nblk) / csize;
+                float2* srow = p.ln_stats + (static_cast<long long>(stripe) * 128 + row) * 8;
+                __stcg(srow + t.n_idx * 2 + half, make_float2(mean_p, m2_p));
+                __threadfence();
+                __syncwarp();
+                unsigned int* cnt = p.ln_count + 2 * stripe;
+                const unsigned int want = 8u * csize;
+                if (lane == 0) {
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+                    unsigned int seen;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    } while (seen < want);
                 }
-                sum = rsqrtf(m2 * inv_n + p.ln_eps);
+                __syncwarp();
+                for (int i = 0; i < npart; ++i) part[i] = __ldcg(srow + i);
+                __syncwarp();
+                if (lane == 0) {   // the last warp to have read the stripe's partials re-arms both counters
+                    unsigned int left;
+                    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(left) : "l"(cnt + 1) : "memory");
+                    if (left == want - 1) {
+                        cnt[1] = 0;
+                        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(0u) : "memory");
+                    }
+                }
             }
-            const float rstd = sum;
+            float mean = 0.0f;
+            for (int i = 0; i < npart; ++i) mean += part[i].x;
+            mean *= 1.0f / static_cast<float>(npart);
+            float m2 = 0.0f;
+            for (int i = 0; i < npart; ++i) {
+                const float d = part[i].x - mean;
+                m2 += part[i].y + kPartN * d * d;
+            }
+            const float rstd = rsqrtf(m2 * inv_n + p.ln_eps);
             // ---- pass 2: normalise, store
             for (int sub = 0; sub < NSUB; ++sub, ++q) {
                 const uint32_t buf = q & 1u;
@@ -856,7 +888,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (LNC) cluster_sync_all();   // no CTA leaves while a peer may still write its statistics buffer
+    if constexpr (LNC) {
+        if (!p.ln_stats) cluster_sync_all();   // no CTA leaves while a peer may still write its statistics buffer
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -902,7 +936,7 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && sm_limit <= 0) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (LNC) {
+    if (LNC && !g->p.ln_stats) {
         // one cluster = the n_tiles_n column tiles of a 128-row stripe; as many clusters as are co-resident
         const int cs = g->p.n_tiles_n;
         attr[1].id = cudaLaunchAttributeClusterDimension;
@@ -920,6 +954,7 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
                 return e != cudaSuccess ? -static_cast<int>(e) : -1;
             }
             max_clusters[cs] = n;
+            if (getenv("MRD_DEBUG_PRINT")) fprintf(stderr, "[mrd] LayerNorm GEMM: %d co-resident clusters of %d CTAs\n", n, cs);
         }
         int clusters = grid / cs;
         if (clusters > max_clusters[cs]) clusters = max_clusters[cs];
@@ -1098,7 +1133,7 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
 
 int plan_gemm_ln(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* W, int N,
                  const float* bias, __nv_bfloat16* Cout, long long ldc, const __nv_bfloat16* residual,
-                 long long ld_res, const float* gamma, const float* beta, float eps) {
+                 long long ld_res, const float* gamma, const float* beta, float eps, void* stats_ws) {
     if (N % 256 != 0 || N / 256 < 2 || N / 256 > 4 || !Cout || !bias || !gamma || !beta) return 1;
     MRD_GEMM_TRY(plan_gemm(g, A, lda, M, K, W, N, bias, Cout, ldc, residual, ld_res, nullptr, 0, ACT_NONE));
     if (g->block_n != 256) return 1;   // few rows: narrower tiles fill the SMs better than clusters of wide ones
@@ -1115,10 +1150,21 @@ int plan_gemm_ln(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, in
         p.stages = 3;
     }
     const int cs = p.n_tiles_n;
-    g->grid = g->grid / cs * cs;
-    if (g->grid < cs) g->grid = cs;
+    if (stats_ws) {
+        const int stripes = (M + 127) / 128;
+        p.ln_count = static_cast<unsigned int*>(stats_ws);
+        p.ln_stats = reinterpret_cast<float2*>(static_cast<char*>(stats_ws) + ((stripes * 8 + 255) & ~255));
+    } else {
+        g->grid = g->grid / cs * cs;
+        if (g->grid < cs) g->grid = cs;
+    }
     g->bytes += 8.0 * N;   // gamma / beta
     return 0;
+}
+
+size_t gemm_ln_ws_bytes(int M) {
+    const size_t stripes = (static_cast<size_t>(M) + 127) / 128;
+    return ((stripes * 8 + 255) & ~static_cast<size_t>(255)) + stripes * 128 * 8 * sizeof(float2);
 }
 
 int plan_gemm_splitk(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,

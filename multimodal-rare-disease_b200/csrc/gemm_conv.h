@@ -70,6 +70,11 @@ struct alignas(64) ConvGemmParams {
     const float* ln_g;
     const float* ln_b;
     float ln_eps;
+    // ln_stats != null: the statistics are exchanged through global memory instead (no cluster launch, every SM
+    // usable): ln_stats [stripes][128][8] (mean, M2) partials, ln_count [stripes][2] arrival / departure counters
+    // (zero between launches: the last warp to leave a stripe resets them).
+    float2* ln_stats;
+    unsigned int* ln_count;
 };
 
 struct GemmLaunch {
@@ -97,9 +102,13 @@ int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int
 // N = c * 256 with c in [2, 4] (BERT-base: 3): a cluster of c CTAs owns a 128-row stripe.  Returns 1 (no error
 // message) when the shape cannot use it (few rows: the plain GEMM picks narrower tiles) - the caller then plans the
 // GEMM and a LayerNorm launch.
+// stats_ws (optional, device, gemm_ln_ws_bytes(M) bytes, zeroed once by the caller): exchange the statistics through
+// global memory - a plain launch on every SM (on B200 only 45 clusters of 3 CTAs with 227 KB of shared memory are
+// co-resident = 135 of 148 SMs); null: thread-block cluster + distributed shared memory.
+size_t gemm_ln_ws_bytes(int M);
 int plan_gemm_ln(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* W, int N,
                  const float* bias, __nv_bfloat16* C, long long ldc, const __nv_bfloat16* residual, long long ld_res,
-                 const float* gamma, const float* beta, float eps);
+                 const float* gamma, const float* beta, float eps, void* stats_ws = nullptr);
 
 // ksize in {1,3}, stride in {1,2}, padding = ksize/2.  X: [N,H,W,Cin] bf16, Wt: [Cout][k][k][Cin]
 // bf16 (BN already folded), Y: [N,H/stride,W/stride,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0.

@@ -30,6 +30,7 @@ configs = {
     "ds+chain": {"split_epilogue": 0, "fuse_chain": 1, "fuse_pool": 0, "fuse_ds": 1},
     "ds+pool": {"split_epilogue": 0, "fuse_chain": 0, "fuse_pool": 1, "fuse_ds": 1},
     "default - fuse_ln": {"split_epilogue": 3, "fuse_chain": 1, "fuse_pool": 1, "fuse_ds": 1, "fuse_ln": 0},
+    "default, fuse_ln=2 (clusters)": {"split_epilogue": 3, "fuse_chain": 1, "fuse_pool": 1, "fuse_ds": 1, "fuse_ln": 2},
     "default - fuse_tail": {"split_epilogue": 3, "fuse_chain": 1, "fuse_pool": 1, "fuse_ds": 1, "fuse_tail": 0},
     "default": {"split_epilogue": 3, "fuse_chain": 1, "fuse_pool": 1, "fuse_ds": 1},
 }
