@@ -142,8 +142,8 @@ int mrd_gemm_bf16(const void* A, long long lda, int M, int K, const void* W, int
 
 /* C = LayerNorm(A W^T + bias + residual) * gamma + beta over whole rows (HF:models/bert/modeling_bert.py:294-298,
  * 352-356: BertSelfOutput / BertOutput) in ONE launch: a thread-block cluster of N/256 CTAs owns a 128-row stripe and
- * exchanges the row statistics through distributed shared memory.  N in {512, 768, 1024}; M large enough that the
- * GEMM uses 256-wide tiles (>= one stripe per SM), otherwise -1.  residual may be NULL.
+ * exchanges the row statistics through distributed shared memory.  N in {512, 768, 1024}, otherwise -1.
+ * residual may be NULL.
  * stats_ws: NULL = the cluster / distributed-shared-memory exchange described above; otherwise a device buffer of
  * mrd_gemm_ln_ws_bytes(M) bytes, zeroed once by the caller, through which the CTAs of a stripe exchange the
  * statistics (plain launch on every SM; only 45 clusters of 3 such CTAs are co-resident on a B200). */

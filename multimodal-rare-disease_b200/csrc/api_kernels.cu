@@ -35,8 +35,7 @@ int mrd_gemm_ln_bf16(const void* A, long long lda, int M, int K, const void* W, 
                           bias, static_cast<__nv_bfloat16*>(C), ldc, static_cast<const __nv_bfloat16*>(residual), ld_res,
                           gamma, beta, eps, stats_ws);
     if (rc > 0) {
-        set_last_error("mrd_gemm_ln_bf16: shape M=%d N=%d outside the fused LayerNorm kernel's range (N = 512 / 768 / "
-                       "1024, enough rows for 256-wide tiles)", M, N);
+        set_last_error("mrd_gemm_ln_bf16: N=%d outside the fused LayerNorm kernel's range (512 / 768 / 1024)", N);
         return -1;
     }
     if (rc) return rc;

@@ -105,6 +105,8 @@ struct TextPlan {
     // last layer, CLS rows only (M = B): everything after its attention feeds nothing but the CLS row
     // (src/text_encoder.py:118), so the out-projection, both LayerNorms and the FFN run on B rows
     GemmLaunch o_cls, f1_cls, f2_cls;
+    GemmLaunch f2_cls_ln;      // the same fused LayerNorm kernel as the full layers' FFN2 (identical arithmetic per row)
+    bool f2_cls_fused = false;
 };
 
 struct BatchPlan {
@@ -854,6 +856,13 @@ int get_text_plan(mrd_ctx* c, int B, int S, TextPlan** out) {
                           c->ffn, nullptr, 0, nullptr, 0, ACT_GELU));
         MRD_TRY(plan_gemm(&p.f2_cls, c->t_cls_ffn, c->ffn, B, c->ffn, L.f2.w, Hd, L.f2.b,
                           c->t_cls_tmp, Hd, c->t_cls_h2, Hd, nullptr, 0, ACT_NONE));
+        if (c->fuse_ln) {
+            // output = this chunk's rows of b_txt: patched at run time (run_bert), planned on a placeholder
+            int r = plan_gemm_ln(&p.f2_cls_ln, c->t_cls_ffn, c->ffn, B, c->ffn, L.f2.w, Hd, L.f2.b, c->t_cls_tmp, Hd,
+                                 c->t_cls_h2, Hd, L.ln2g, L.ln2b, c->bert_ln_eps, c->fuse_ln == 1 ? c->t_ln_ws : nullptr);
+            if (r < 0) return r;
+            p.f2_cls_fused = r == 0;
+        }
     }
     auto ins = c->text_plans.emplace(key, std::move(p));
     *out = &ins.first->second;
@@ -1193,8 +1202,15 @@ int run_bert(mrd_ctx* c, const long long* ids, const void* mask, int mask_dtype,
                                                c->bert_ln_eps, nb, Hd, c->t_cls_h2, Hd, nullptr, 0, s));
                 }
                 MRD_TRY(run(c, "bert.cls.ffn1+gelu", p->f1_cls, s));
-                MRD_TRY(run(c, "bert.cls.ffn2+res", p->f2_cls, s));
-                {
+                if (p->f2_cls_fused) {
+                    MRD_TRY(run(c, "bert.cls.ffn2+res+ln", p->f2_cls_ln, s));
+                    // the plan's output is a workspace row block: copy to this chunk's rows of the embedding buffer
+                    ProfScope ps(c, s, "cls_copy", CAT_MEM, 0, 4.0 * nb * Hd);
+                    cudaError_t e = cudaMemcpyAsync(c->b_txt + 1LL * b0 * Hd, c->t_cls_tmp, sizeof(bf16) * nb * Hd,
+                                                    cudaMemcpyDeviceToDevice, s);
+                    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(CLS rows)");
+                } else {
+                    MRD_TRY(run(c, "bert.cls.ffn2+res", p->f2_cls, s));
                     ProfScope ps(c, s, "bert.cls.layernorm", CAT_MEM, 0, 4.0 * nb * Hd);
                     MRD_TRY(layernorm_residual(c->t_cls_tmp, Hd, nullptr, 0, L.ln2g, L.ln2b,
                                                c->bert_ln_eps, nb, Hd, c->b_txt + 1LL * b0 * Hd, Hd,
@@ -1380,6 +1396,10 @@ int mrd_ctx_set_option(mrd_ctx* c, const char* key, double v) {
     else if (k == "fuse_tail") { c->fuse_tail = v != 0.0; c->batch_plans.clear(); }
     else if (k == "fuse_pool") { c->fuse_pool = v != 0.0; c->cnn_plans.clear(); }
     else if (k == "fuse_chain") { c->fuse_chain = static_cast<int>(v); c->cnn_plans.clear(); }
+    else if (k == "pair_gemm") {   // process-wide A/B switch; plans are rebuilt
+        gemm_set_pair(static_cast<int>(v));
+        c->cnn_plans.clear(); c->text_plans.clear(); c->batch_plans.clear();
+    }
     else if (k == "split_epilogue") gemm_set_split_epilogue(static_cast<int>(v));   // process-wide A/B switch
     else if (k == "chain_tuning") {   // process-wide A/B switch: value = lag * 8 + hints (conv_chain.h)
         conv_chain_set_tuning(static_cast<int>(v) / 8, static_cast<int>(v) % 8);

@@ -31,6 +31,7 @@ namespace mrd {
 namespace {
 
 bool g_use_pdl = true;
+int g_pair_gemm = 1;        // flat GEMMs with 256-wide tiles and many stripes: two-CTA clusters sharing the weight tile (PAIR)
 int g_split_epilogue = 3;   // two-group epilogue (EPI2): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem
 
 // Debugging overrides (tools/stress_kernels.py): MRD_DEBUG_SPLIT_EPILOGUE, MRD_DEBUG_PDL, MRD_DEBUG_RING, read once.
@@ -42,6 +43,7 @@ void apply_debug_env() {
     if (const char* e = getenv("MRD_DEBUG_SPLIT_EPILOGUE")) g_split_epilogue = atoi(e);
     if (const char* e = getenv("MRD_DEBUG_PDL")) g_use_pdl = atoi(e) != 0;
     if (const char* e = getenv("MRD_DEBUG_RING")) g_debug_ring = atoi(e);
+    if (const char* e = getenv("MRD_DEBUG_PAIR")) g_pair_gemm = atoi(e);
 }
 
 constexpr int kBlockM = 128;
@@ -110,8 +112,21 @@ constexpr int kStemRows = 37;
 // (st.shared::cluster) and counted on an mbarrier there.  Pass 2: combine the partials (Chan), normalise the TMEM
 // values, store.  HF:models/bert/modeling_bert.py:294-298,352-356.
 constexpr int kLnStatBytes = 2 * 128 * 8 * 8;   // two buffers x 128 rows x up to 8 partials x (mean, M2)
+// exchange through L2: one record per 128-row stripe = 128 rows x 8 partials x (mean, M2), then the arrival / departure
+// counters.  The layout does not depend on the row count, so plans of different sizes can share one workspace.
+constexpr int kLnStripeBytes = 128 * 8 * 8 + 64;
 
-template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false>
+// PAIR (generic mode, flat GEMMs): tcgen05.mma.cta_group::2.  A cluster of two CTAs takes the 128-row stripes 2j and
+// 2j+1 of the SAME column tile as ONE 256 x 256 tile: each CTA's producer loads its own 128 x 64 A block and HALF of
+// the 256 x 64 weight block per K step (32 KB instead of 48 KB into each SM: a single-CTA 128 x 256 tile needs
+// 94 B/clk of L2 -> SM ingest at full tensor rate, which the SM port does not deliver - the BERT GEMMs sat at ~62 % of
+// the tensor rate, r02), the leader CTA's MMA warp issues 256 x 256 x 16 instructions that read both CTAs' shared
+// memory and write both CTAs' TMEM, and its tcgen05.commit arrives on the barriers of both CTAs (.multicast::cluster).
+// The peer CTA's warp 1 forwards "my stage has landed" to the leader (remote mbarrier arrive); both CTAs' epilogue
+// warps hand an accumulator back by arriving on the LEADER's `tempty` barrier.  (Measured first: only multicasting the
+// weight tile into both CTAs, each still issuing its own 128 x 256 MMAs, changed nothing - the bytes into each SM
+// stayed the same.)
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BLOCK_N, MODE>;
@@ -127,7 +142,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // tensor core for only 32 cycles; a barrier round trip per 64-wide K block (the generic path)
     // makes such layers issue-bound.
     const int a_stage_bytes = WRES ? p.a_stage_bytes : C::A_STAGE;
-    const int b_region = WRES ? p.b_res_bytes : STAGES * C::B_STAGE;
+    constexpr int B_STAGE = PAIR ? C::B_STAGE / 2 : C::B_STAGE;   // PAIR: each CTA holds half of the weight block
+    const int b_region = WRES ? p.b_res_bytes : STAGES * B_STAGE;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -150,6 +166,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     auto rempty_bar = [&](int s) { return bar_smem + 192u + 8u * s; };
     auto tfull_bar = [&](int a) { return bar_smem + 256u + 8u * a; };
     auto tempty_bar = [&](int a) { return bar_smem + 272u + 8u * a; };
+    // hand accumulator stage a back to the MMA issuer (PAIR: the leader CTA's barrier counts both CTAs' warps)
+    auto release_acc = [&](int a) {
+        if constexpr (PAIR)
+            mbar_arrive_remote(mapa_shared(tempty_bar(a), 0));
+        else
+            mbar_arrive(tempty_bar(a));
+    };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,6 +185,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
+            if constexpr (PAIR) mbar_init(bar_smem + 448u + 8u * s, 1);   // leader: the peer's stage s has landed
             mbar_init(rfull_bar(s), 1);
             // ONE arrival per consumed sub-tile, made by the thread that issues the sub-tile's TMA store, i.e. after
             // every consumer thread has turned the residual into shared-memory stores behind a barrier.  An arrival
@@ -174,7 +198,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
             // one arrival per epilogue warp and accumulator (EPI2: four warps per 64-column sub-tile)
-            mbar_init(tempty_bar(a), EPI2 ? 4 * (BLOCK_N / 64) : 8);
+            mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * (EPI2 ? 4 * (BLOCK_N / 64) : 8));
         }
         mbar_init(bres_bar, 1);
         if constexpr (LNC) {   // statistics of one stripe have arrived: one arrival per epilogue warp of the cluster
@@ -183,13 +207,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(bar_smem + 320);
+    if (warp == 1) {
+        if constexpr (PAIR)
+            tmem_alloc_pair<C::TMEM_COLS>(bar_smem + 320);
+        else
+            tmem_alloc<C::TMEM_COLS>(bar_smem + 320);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if constexpr (LNC) {
-        if (!p.ln_stats) cluster_sync_all();   // the peers' barriers exist before anyone arrives on them
+    if constexpr (LNC || PAIR) {
+        if (PAIR || !p.ln_stats) cluster_sync_all();   // the peers' barriers exist before anyone arrives on them
     }
 
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
@@ -209,7 +238,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     const int box_rows = p.tw * p.th * p.nb;
     const uint32_t a_box_bytes = static_cast<uint32_t>(box_rows) * C::ROW_BYTES;
-    const uint32_t stage_tx = a_box_bytes + C::B_STAGE;
+    const uint32_t stage_tx = a_box_bytes + B_STAGE;
     const int bid = static_cast<int>(blockIdx.x), nblk = static_cast<int>(gridDim.x);
     // token-packed BERT: the live row count is only known on the device
     int total_tiles = p.total_tiles;
@@ -225,7 +254,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         ksplit = ksplit < num_k ? ksplit : num_k;
     }
     const int total_items = SPLITK ? total_tiles * ksplit : total_tiles;
-    const int my_tiles = total_items > bid ? (total_items - bid + nblk - 1) / nblk : 0;
+    int my_tiles = total_items > bid ? (total_items - bid + nblk - 1) / nblk : 0;
+    // work item `it` of this CTA -> tile.  PAIR: cluster c of P takes pair-tiles j = c + it * P of
+    // ceil(stripes / 2) x n_tiles_n; j = (stripe pair, column tile); CTA rank r works on stripe 2 * pair + r.  With an
+    // odd stripe count the last pair's second tile lies outside the matrix: its loads are zero-filled, its stores
+    // clipped by the tensor maps, and it still forwards its half of the weight tiles.
+    uint32_t pair_rank = 0;
+    if constexpr (PAIR) {
+        pair_rank = cluster_ctarank();
+        const int pair_total = (total_tiles / p.n_tiles_n + 1) / 2 * p.n_tiles_n;
+        const int c = bid >> 1, P = nblk >> 1;
+        my_tiles = pair_total > c ? (pair_total - c + P - 1) / P : 0;
+    }
+    auto tile_at = [&](int it) -> int {
+        if constexpr (PAIR) {
+            const int j = (bid >> 1) + it * (nblk >> 1);
+            const int pm = j / p.n_tiles_n;
+            return (2 * pm + static_cast<int>(pair_rank)) * p.n_tiles_n + (j - pm * p.n_tiles_n);
+        } else {
+            return bid + it * nblk;
+        }
+    };
 
     if (warp == 0 && WRES) {
         // ------------------------------------------------------------ TMA producer, weights-resident modes
@@ -361,7 +410,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = bid; item < total_items; item += nblk) {
+        for (int pit = 0; pit < my_tiles; ++pit) {
+            const int item = tile_at(pit);
             const int split = SPLITK ? item / total_tiles : 0;
             const TileCoord t = decode_tile(p, SPLITK ? item - split * total_tiles : item);
             const int k_begin = SPLITK ? split * num_k / ksplit : 0;
@@ -371,15 +421,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 if (lane == 0) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t a_dst = a_smem + stage * C::A_STAGE;
-                    const uint32_t b_dst = b_smem + stage * C::B_STAGE;
+                    const uint32_t b_dst = b_smem + stage * B_STAGE;
                     // K-concatenated pair of 1x1 convolutions: chunks [0, kc_split) read taps[0], the rest taps[1]
                     const int tap = p.kc_split ? (ks >= p.kc_split ? 1 : 0) : ks / p.kc_per_tap;
                     const int kc = ks - tap * (p.kc_split ? p.kc_split : p.kc_per_tap);
                     const TapDesc td = p.taps[tap];
                     tma_load_4d(&p.a_map[td.map], full_bar(stage), a_dst, kc * C::BLOCK_K,
                                 t.w0 + td.dw, t.h0 + td.dh, t.n0);
+                    // PAIR: my half of the weight block (b_map's box is BLOCK_N / 2 rows)
                     tma_load_2d(&p.b_map, full_bar(stage), b_dst, ks * C::BLOCK_K,
-                                t.n_idx * BLOCK_N);
+                                t.n_idx * BLOCK_N + (PAIR ? static_cast<int>(pair_rank) * (BLOCK_N / 2) : 0));
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -387,14 +438,25 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int item = bid; item < total_items; item += nblk, ++it) {
+        if (PAIR && pair_rank != 0) {
+            // peer CTA: no MMAs of its own - tell the leader when each of my stages has landed (the TMA's bytes are
+            // visible to me through the barrier wait, to the leader through the release / acquire pair at cluster scope)
+            for (int it = 0; it < my_tiles; ++it)
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
+                    if (lane == 0) mbar_arrive_remote(mapa_shared(bar_smem + 448u + 8u * stage, 0));
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+        } else
+        for (int it = 0; it < my_tiles; ++it) {
+            const int item = tile_at(it);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // PAIR: both CTAs' epilogues have drained it
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             const int split = SPLITK ? item / total_tiles : 0;
@@ -402,20 +464,32 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int k_end = SPLITK ? (split + 1) * num_k / ksplit : num_k;
             for (int ks = k_begin; ks < k_end; ++ks) {
                 mbar_wait(full_bar(stage), phase);
+                // (plain waits on the remotely-arrived barriers, as for any cluster barrier: an acquire at cluster scope
+                // per K step cost more than the step's 512 tensor cycles and held the pair at 700 TFLOP/s)
+                if constexpr (PAIR) mbar_wait(bar_smem + 448u + 8u * stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint64_t adesc =
                         make_smem_desc(a_smem + stage * C::A_STAGE, 0, C::SBO, C::LAYOUT);
                     const uint64_t bdesc =
-                        make_smem_desc(b_smem + stage * C::B_STAGE, 0, C::SBO, C::LAYOUT);
+                        make_smem_desc(b_smem + stage * B_STAGE, 0, C::SBO, C::LAYOUT);
 #pragma unroll
                     for (int k = 0; k < C::BLOCK_K / 16; ++k) {
                         // +32 bytes (encoded >>4) per 16-element K slice inside the swizzle span
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                  (ks != k_begin || k != 0) ? 1u : 0u);
+                        if constexpr (PAIR)
+                            umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                           (ks != k_begin || k != 0) ? 1u : 0u);
+                        else
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                      (ks != k_begin || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));
-                    if (ks == k_end - 1) umma_commit(tfull_bar(acc));
+                    if constexpr (PAIR) {   // the stage is free, the accumulator ready: in BOTH CTAs
+                        umma_commit_pair(empty_bar(stage), 3);
+                        if (ks == k_end - 1) umma_commit_pair(tfull_bar(acc), 3);
+                    } else {
+                        umma_commit(empty_bar(stage));
+                        if (ks == k_end - 1) umma_commit(tfull_bar(acc));
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -430,7 +504,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             int slot = 0;
             uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                const TileCoord t = decode_tile(p, SPLITK ? (bid + it * nblk) % total_tiles : bid + it * nblk);
+                const TileCoord t = decode_tile(p, SPLITK ? tile_at(it) % total_tiles : tile_at(it));
                 for (int sub = 0; sub < NSUB; ++sub) {
                     mbar_wait(rempty_bar(slot), phase ^ 1u);
                     if (lane == 0) {
@@ -463,7 +537,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int q = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1, sb = it & 1;
-            const TileCoord t = decode_tile(p, bid + it * nblk);
+            const TileCoord t = decode_tile(p, tile_at(it));
             const uint32_t tbase =
                 tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * 32;
             mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
@@ -532,12 +606,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             } else {
                 // through L2: the csize CTAs of a stripe are neighbours in the persistent tile order, so all of them
                 // are resident (grid <= SM count) and a spin on the stripe's arrival counter cannot deadlock
-                const int stripe = (bid + it * nblk) / csize;
-                float2* srow = p.ln_stats + (static_cast<long long>(stripe) * 128 + row) * 8;
+                const int stripe = tile_at(it) / csize;
+                char* rec = reinterpret_cast<char*>(p.ln_stats) + static_cast<long long>(stripe) * kLnStripeBytes;
+                float2* srow = reinterpret_cast<float2*>(rec) + row * 8;
                 __stcg(srow + t.n_idx * 2 + half, make_float2(mean_p, m2_p));
                 __threadfence();
                 __syncwarp();
-                unsigned int* cnt = p.ln_count + 2 * stripe;
+                unsigned int* cnt = reinterpret_cast<unsigned int*>(rec + 128 * 8 * 8);
                 const unsigned int want = 8u * csize;
                 if (lane == 0) {
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
@@ -579,7 +654,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 if (sub == NSUB - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) release_acc(acc);
                 }
                 float f[32];
 #pragma unroll
@@ -631,7 +706,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int sub = q % NSUB;
             const int it = q / NSUB;
             const int acc = it & 1;
-            const TileCoord t = decode_tile(p, bid + it * nblk);
+            const TileCoord t = decode_tile(p, tile_at(it));
             const int col0 = t.n_idx * BLOCK_N + sub * 64;
             mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
             tc_fence_after();
@@ -642,7 +717,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) release_acc(acc);
             float f[64];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -776,13 +851,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int rslot = 0;
         uint32_t rphase = 0;
 
-        TileCoord t = decode_tile(p, SPLITK ? (total_tiles > 0 ? bid % total_tiles : 0) : bid);
+        TileCoord t = decode_tile(p, SPLITK ? (total_tiles > 0 ? bid % total_tiles : 0) : tile_at(0));
         for (int q = 0; q < nq; ++q) {
             const int sub = q % NSUB;
             const int it = q / NSUB;
             const int acc = it & 1;
             const uint32_t buf = q & 1u;
-            if (sub == 0) t = decode_tile(p, SPLITK ? (bid + it * nblk) % total_tiles : bid + it * nblk);
+            if (sub == 0) t = decode_tile(p, SPLITK ? tile_at(it) % total_tiles : tile_at(it));
             const int col0 = t.n_idx * BLOCK_N + sub * 64 + half * 32;  // first global column of this thread
 
             if (sub == 0) {
@@ -798,7 +873,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 // accumulator stage fully read by this warp: hand it back to the MMA warp early
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (lane == 0) release_acc(acc);
             }
             float f[32];
 #pragma unroll
@@ -888,20 +963,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (LNC) {
-        if (!p.ln_stats) cluster_sync_all();   // no CTA leaves while a peer may still write its statistics buffer
+    if constexpr (LNC || PAIR) {
+        // no CTA leaves while a peer may still write its statistics buffer / arrive on its barriers
+        if (PAIR || !p.ln_stats) cluster_sync_all();
     }
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+        if constexpr (PAIR)
+            tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+        else
+            tmem_dealloc<C::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false>
+template <int BLOCK_N, int MODE, bool SPLITK = false, bool EPI2 = false, bool LNC = false, bool PAIR = false>
 int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     using C = Cfg<BLOCK_N, MODE>;
     static bool attr_set = false;
-    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK, EPI2, LNC>;
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLITK, EPI2, LNC, PAIR>;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -913,7 +992,8 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     }
     const int smem = MODE != MODE_GENERIC
                          ? C::FIXED + g->p.stages * g->p.a_stage_bytes + g->p.b_res_bytes
-                         : C::FIXED + g->p.stages * C::STAGE + g->p.ring * kStageBufBytes + (LNC ? kLnStatBytes : 0);
+                         : C::FIXED + g->p.stages * (PAIR ? C::A_STAGE + C::B_STAGE / 2 : C::STAGE) +
+                               g->p.ring * kStageBufBytes + (LNC ? kLnStatBytes : 0);
     cudaLaunchConfig_t cfg = {};
     int grid = g->grid;
     if (sm_limit > 0 && grid > sm_limit) {
@@ -936,9 +1016,10 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && sm_limit <= 0) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (LNC && !g->p.ln_stats) {
-        // one cluster = the n_tiles_n column tiles of a 128-row stripe; as many clusters as are co-resident
-        const int cs = g->p.n_tiles_n;
+    if (PAIR || (LNC && !g->p.ln_stats)) {
+        // LNC: one cluster = the n_tiles_n column tiles of a 128-row stripe; PAIR: two stripes of one column tile.
+        // As many clusters as are co-resident.
+        const int cs = PAIR ? 2 : g->p.n_tiles_n;
         attr[1].id = cudaLaunchAttributeClusterDimension;
         attr[1].val.clusterDim.x = cs;
         attr[1].val.clusterDim.y = 1;
@@ -954,7 +1035,9 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
                 return e != cudaSuccess ? -static_cast<int>(e) : -1;
             }
             max_clusters[cs] = n;
-            if (getenv("MRD_DEBUG_PRINT")) fprintf(stderr, "[mrd] LayerNorm GEMM: %d co-resident clusters of %d CTAs\n", n, cs);
+            if (getenv("MRD_DEBUG_PRINT"))
+                fprintf(stderr, "[mrd] conv_gemm_kernel<%d,%d,%d,%d,%d,%d>: %d co-resident clusters of %d CTAs\n", BLOCK_N,
+                        MODE, SPLITK, EPI2, LNC, PAIR, n, cs);
         }
         int clusters = grid / cs;
         if (clusters > max_clusters[cs]) clusters = max_clusters[cs];
@@ -972,8 +1055,8 @@ int launch_variant(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
 }
 
 // Pipeline depths for one launch: operand stages vs residual ring (both live in the same 227 KB).
-void pick_pipeline(ConvGemmParams* p, int block_n, bool stem) {
-    const int stage = stem ? (128 * 64 + 64 * 64) : (128 * 128 + block_n * 128);
+void pick_pipeline(ConvGemmParams* p, int block_n, bool stem, bool pair = false) {
+    const int stage = stem ? (128 * 64 + 64 * 64) : (128 * 128 + (pair ? block_n / 2 : block_n) * 128);
     const int fixed = 2 * kStageBufBytes + kBarBytes + 1024;
     const int avail = kSmemLimit - fixed;
     const int num_k = p->num_taps * p->kc_per_tap;
@@ -992,6 +1075,11 @@ void pick_pipeline(ConvGemmParams* p, int block_n, bool stem) {
         r = kMaxRing;
         int extra = (avail - r * kStageBufBytes) / stage;  // leftover smem back to the operand pipeline
         if (extra > s) s = extra > kMaxStages ? kMaxStages : extra;
+    }
+    if (num_k > 6 && r > 4) {   // long K: one tile's residual sub-tiles in flight are enough, the rest feeds the operands
+        r = 4;
+        int more = (avail - r * kStageBufBytes) / stage;
+        if (more > s) s = more > kMaxStages ? kMaxStages : more;
     }
     apply_debug_env();
     if (g_debug_ring > 0 && g_debug_ring < r) r = g_debug_ring;
@@ -1032,7 +1120,7 @@ int finish_plan(GemmLaunch* g, int block_n) {
         g->grid = g->grid / p.n_tiles_n * p.n_tiles_n;
         if (g->grid < p.n_tiles_n) g->grid = p.n_tiles_n;
     } else {
-        pick_pipeline(&p, block_n, false);
+        pick_pipeline(&p, block_n, false, g->pair != 0);
     }
     return 0;
 }
@@ -1041,6 +1129,7 @@ int finish_plan(GemmLaunch* g, int block_n) {
 
 void gemm_set_pdl(bool on) { g_use_pdl = on; }
 void gemm_set_split_epilogue(int mask) { g_split_epilogue = mask; }
+void gemm_set_pair(int on) { g_pair_gemm = on; }
 
 int gemm_num_sms() {
     static int sms = 0;
@@ -1054,10 +1143,25 @@ int gemm_num_sms() {
     return sms;
 }
 
+namespace {
+int plan_gemm_impl(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
+                   const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* Cout, long long ldc,
+                   const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
+                   int act, int c_blocked, int force_bn);
+}
+
 int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
               const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* Cout, long long ldc,
               const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
               int act, int c_blocked) {
+    return plan_gemm_impl(g, A, lda, M, K, W, N, bias, Cout, ldc, residual, ld_res, out_f32, ld_f32, act, c_blocked, 0);
+}
+
+namespace {
+int plan_gemm_impl(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
+                   const __nv_bfloat16* W, int N, const float* bias, __nv_bfloat16* Cout, long long ldc,
+                   const __nv_bfloat16* residual, long long ld_res, float* out_f32, long long ld_f32,
+                   int act, int c_blocked, int force_bn) {
     memset(g, 0, sizeof(*g));
     if (M <= 0 || K <= 0 || N <= 0 || K % 64 != 0 || N % 64 != 0 || lda % 8 != 0 ||
         (Cout && ldc % 8 != 0)) {
@@ -1083,7 +1187,11 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     g->bytes = 2.0 * (1.0 * M * K + 1.0 * N * K + (Cout ? 1.0 * M * N : 0.0) + (residual ? 1.0 * M * N : 0.0)) +
                (out_f32 ? 4.0 * M * N : 0.0);
 
-    const int bn = pick_block_n(N, p.tiles_w, gemm_num_sms());
+    const int bn = force_bn ? force_bn : pick_block_n(N, p.tiles_w, gemm_num_sms());
+    apply_debug_env();
+    // at least two tiles per SM: below that the pairing has nothing to amortise
+    if (const char* e = getenv("MRD_DEBUG_FLAGS")) p.debug = atoi(e);
+    g->pair = (g_pair_gemm && bn == 256 && static_cast<long long>(p.tiles_w) * (N / 256) >= 2LL * gemm_num_sms()) ? 1 : 0;
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
         uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * M, (uint64_t)lda * 2 * M};
@@ -1095,7 +1203,7 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)K * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(g->pair ? bn / 2 : bn)};   // PAIR: each CTA fetches half a weight tile
         int rc = encode_tensor_map(&p.b_map, W, 2, 2, dims, str, box, 128);
         if (rc) return rc;
     }
@@ -1130,30 +1238,39 @@ int plan_gemm(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K
     }
     return finish_plan(g, bn);
 }
+}  // namespace
 
 int plan_gemm_ln(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* W, int N,
                  const float* bias, __nv_bfloat16* Cout, long long ldc, const __nv_bfloat16* residual,
                  long long ld_res, const float* gamma, const float* beta, float eps, void* stats_ws) {
     if (N % 256 != 0 || N / 256 < 2 || N / 256 > 4 || !Cout || !bias || !gamma || !beta) return 1;
-    MRD_GEMM_TRY(plan_gemm(g, A, lda, M, K, W, N, bias, Cout, ldc, residual, ld_res, nullptr, 0, ACT_NONE));
-    if (g->block_n != 256) return 1;   // few rows: narrower tiles fill the SMs better than clusters of wide ones
+    // always 256-wide tiles, however few rows there are: which kernel (and so which rounding) a row goes through
+    // must not depend on the batch it arrives in - sub-batches reproduce the rows of the full batch bit for bit
+    MRD_GEMM_TRY(plan_gemm_impl(g, A, lda, M, K, W, N, bias, Cout, ldc, residual, ld_res, nullptr, 0, ACT_NONE, 0, 256));
     ConvGemmParams& p = g->p;
+    if (g->pair && !stats_ws) {   // the cluster is taken by the statistics exchange: whole weight tiles per CTA
+        g->pair = 0;
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)K * 2};
+        uint32_t box[2] = {64, 256};
+        int rc = encode_tensor_map(&p.b_map, W, 2, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
     p.ln_g = gamma;
     p.ln_b = beta;
     p.ln_eps = eps;
     g->lnc = 1;
-    // room for the statistics buffers: three operand stages, two residual sub-tiles in flight
+    // room for the statistics buffers: three operand stages (four of the pair's smaller ones), two residual
+    // sub-tiles in flight
     if (p.has_res) {
-        p.stages = 3;
+        p.stages = g->pair ? 4 : 3;
         p.ring = 2;
-    } else if (p.stages > 3) {
-        p.stages = 3;
+    } else if (p.stages > (g->pair ? 5 : 3)) {
+        p.stages = g->pair ? 5 : 3;
     }
     const int cs = p.n_tiles_n;
     if (stats_ws) {
-        const int stripes = (M + 127) / 128;
-        p.ln_count = static_cast<unsigned int*>(stats_ws);
-        p.ln_stats = reinterpret_cast<float2*>(static_cast<char*>(stats_ws) + ((stripes * 8 + 255) & ~255));
+        p.ln_stats = static_cast<float2*>(stats_ws);   // records of kLnStripeBytes
     } else {
         g->grid = g->grid / cs * cs;
         if (g->grid < cs) g->grid = cs;
@@ -1163,8 +1280,8 @@ int plan_gemm_ln(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, in
 }
 
 size_t gemm_ln_ws_bytes(int M) {
-    const size_t stripes = (static_cast<size_t>(M) + 127) / 128;
-    return ((stripes * 8 + 255) & ~static_cast<size_t>(255)) + stripes * 128 * 8 * sizeof(float2);
+    const size_t stripes = ((static_cast<size_t>(M) + 127) / 128 + 1) & ~static_cast<size_t>(1);
+    return stripes * kLnStripeBytes;   // (even stripe count: the pair's second stripe may lie outside the matrix)
 }
 
 int plan_gemm_splitk(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, int K,
@@ -1177,6 +1294,7 @@ int plan_gemm_splitk(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M
     // plan_gemm sized the N tile for a single pass (64 wide when there are few tiles); with split-K the SMs
     // are filled by K slices instead, so take the widest tile (best operand reuse) and rebuild the B map
     const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+    g->pair = 0;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)K * 2};
@@ -1587,7 +1705,9 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
         if ((g_split_epilogue & 4) || g->p.pool_out) return launch_variant<64, MODE_STEM, false, true>(g, stream, sm_limit);
         return launch_variant<64, MODE_STEM>(g, stream, sm_limit);
     }
-    if (g->lnc) return launch_variant<256, MODE_GENERIC, false, false, true>(g, stream, sm_limit);
+    if (g->lnc)
+        return g->pair ? launch_variant<256, MODE_GENERIC, false, false, true, true>(g, stream, sm_limit)
+                       : launch_variant<256, MODE_GENERIC, false, false, true>(g, stream, sm_limit);
     if (g->flat3 && (g_split_epilogue & 2)) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_FLAT3, false, true>(g, stream, sm_limit);
@@ -1614,7 +1734,12 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     // single-group epilogue with its two shared staging buffers (QKV lost 5 % with the split).
     const bool chain_bound = g->p.act == ACT_GELU || g->p.num_taps * g->p.kc_per_tap <= 6 ||
                              (g->p.kc_split && g->p.num_k_total <= 6);
-    if ((g_split_epilogue & 1) && chain_bound && !(g->p.kc_split && g->p.num_k_total > 6)) {
+    const bool epi2 = (g_split_epilogue & 1) && chain_bound && !(g->p.kc_split && g->p.num_k_total > 6);
+    if (g->pair && g->block_n == 256) {
+        if (epi2) return launch_variant<256, MODE_GENERIC, false, true, false, true>(g, stream, sm_limit);
+        return launch_variant<256, MODE_GENERIC, false, false, false, true>(g, stream, sm_limit);
+    }
+    if (epi2) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_GENERIC, false, true>(g, stream, sm_limit);
             case 128: return launch_variant<128, MODE_GENERIC, false, true>(g, stream, sm_limit);

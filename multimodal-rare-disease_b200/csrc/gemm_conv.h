@@ -71,10 +71,10 @@ struct alignas(64) ConvGemmParams {
     const float* ln_b;
     float ln_eps;
     // ln_stats != null: the statistics are exchanged through global memory instead (no cluster launch, every SM
-    // usable): ln_stats [stripes][128][8] (mean, M2) partials, ln_count [stripes][2] arrival / departure counters
-    // (zero between launches: the last warp to leave a stripe resets them).
+    // usable): one record per 128-row stripe = [128][8] (mean, M2) partials + arrival / departure counters (zero
+    // between launches: the last warp to leave a stripe resets them).
     float2* ln_stats;
-    unsigned int* ln_count;
+    int debug;   // timing experiments only (MRD_DEBUG_FLAGS): bit 0 = the pair leader does not wait for the peer's stages
 };
 
 struct GemmLaunch {
@@ -83,6 +83,7 @@ struct GemmLaunch {
     int stem;     // 1: 5-D overlapping-window A map, BLOCK_K = 32
     int flat3;    // 1: flat-shift 3x3 stride-1 mode (halo span in smem, taps = row-shifted views)
     int lnc;      // 1: LayerNorm epilogue across a cluster of n_tiles_n CTAs (plan_gemm_ln)
+    int pair;     // 1: two-CTA clusters sharing each weight tile by TMA multicast (b_map's box is half a tile)
     int grid;
     double flops;  // algorithmic FLOPs (2*M*N*K, un-padded), for reporting
     double bytes;  // algorithmic bytes: A + W read once, C written once (+ residual read)
@@ -99,9 +100,8 @@ int plan_gemm(GemmLaunch* out, const __nv_bfloat16* A, long long lda, int M, int
 
 // C = LayerNorm(A W^T + bias + residual) over the whole row (nn.LayerNorm(N), eps), gamma / beta fp32 [N]:
 // HF:models/bert/modeling_bert.py:294-298,352-356 (dense -> dropout -> LayerNorm(x + input)) as ONE launch.
-// N = c * 256 with c in [2, 4] (BERT-base: 3): a cluster of c CTAs owns a 128-row stripe.  Returns 1 (no error
-// message) when the shape cannot use it (few rows: the plain GEMM picks narrower tiles) - the caller then plans the
-// GEMM and a LayerNorm launch.
+// N = c * 256 with c in [2, 4] (BERT-base: 3): c CTAs own a 128-row stripe.  Returns 1 (no error message) when N
+// is outside that range - the caller then plans the GEMM and a LayerNorm launch.
 // stats_ws (optional, device, gemm_ln_ws_bytes(M) bytes, zeroed once by the caller): exchange the statistics through
 // global memory - a plain launch on every SM (on B200 only 45 clusters of 3 CTAs with 227 KB of shared memory are
 // co-resident = 135 of 148 SMs); null: thread-block cluster + distributed shared memory.
@@ -162,5 +162,7 @@ int gemm_num_sms();
 void gemm_set_pdl(bool on);
 // Two-group epilogue (process-wide A/B switch): bit 0 generic-mode launches, bit 1 flat 3x3, bit 2 stem.
 void gemm_set_split_epilogue(int mask);
+// process-wide A/B switch for plans made afterwards: pair the 128-row stripes of large flat GEMMs (PAIR)
+void gemm_set_pair(int on);
 
 }  // namespace mrd

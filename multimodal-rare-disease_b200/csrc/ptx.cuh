@@ -201,6 +201,38 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
                  : "memory");
 }
 
+// cta_group::2: TMEM columns in BOTH CTAs of a pair (one warp of each CTA executes these)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result_addr) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// One 256 x N x 16 product over the CTA pair, issued by ONE thread of the leader CTA: each CTA's shared memory holds
+// 128 rows of A and N/2 rows of B at the offsets the descriptors name, each CTA's TMEM gets its 128 accumulator rows
+// (verified by tools/exp_cta_pair.cu).
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of cta_mask when the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32, issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -274,9 +306,32 @@ __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a,
 __device__ __forceinline__ void fence_acq_rel_cluster() {
     asm volatile("fence.acq_rel.cluster;" ::: "memory");
 }
+// TMA load delivered to the same shared-memory offset (and counted on the same mbarrier offset) of every CTA of the
+// cluster whose bit is set in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(const void* map, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
+}
 // arrive on an mbarrier of another CTA of the cluster (address from mapa_shared), release at cluster scope
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// the same with the default (CTA-scope release) ordering: for barriers that only pace hardware-tracked work - a TMA
+// landing, accumulator columns drained with tcgen05.ld - and publish no data written by ordinary stores.  (The
+// cluster-scope release above costs the arriving thread on the order of a thousand cycles per call.)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // wait on a local mbarrier whose arrivals come from other CTAs: acquire at cluster scope
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
