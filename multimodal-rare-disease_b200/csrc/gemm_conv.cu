@@ -1063,6 +1063,10 @@ void pick_pipeline(ConvGemmParams* p, int block_n, bool stem, bool pair = false)
     if (!p->has_res) {
         int s = avail / stage;
         p->stages = s > kMaxStages ? kMaxStages : s;
+        if (const char* e = getenv("MRD_DEBUG_STAGES")) {   // timing experiments: a shallower operand pipeline
+            const int v = atoi(e);
+            if (v >= 2 && v < p->stages) p->stages = v;
+        }
         p->ring = 0;
         return;
     }

@@ -385,23 +385,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 // Exact-erf GELU (HF:activations.py:70-90) with erf from Abramowitz & Stegun 7.1.26
 // (|error| <= 1.5e-7, far below the bf16 rounding of the result), written against the raw fast-math
-// units: one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner chain = 16 issue slots per element, so the
-// FFN1 epilogue keeps pace with the tensor core (erff(), or __fdividef/__expf with their range
-// fix-ups, cost 2-3x as many).
+// units: one MUFU.RCP, one MUFU.EX2 and 11 FP32 issue slots per element, so the FFN1 epilogue keeps pace with the
+// tensor core (erff(), or __fdividef/__expf with their range fix-ups, cost 2-3x as many).
 //   z = |x|/sqrt(2), t = 1/(1 + p z), h = 0.5 (a1 t + ... + a5 t^5) exp(-z^2) = 0.5 erfc(z)
-//   gelu(x) = x * (x >= 0 ? 1 - h : h)
+//   gelu(x) = x (x >= 0 ? 1 - h : h) = max(x, 0) - |x| h
+// with w = |x| sqrt(log2(e)/2): exp(-z^2) = 2^(-w^2) and p z = (p sqrt(2/log2(e)) / sqrt(2)) w, so |x| is scaled once.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     float t, e;
-    const float z = fabsf(x) * 0.70710678118654752f;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    // exp(-z^2) = 2^(-x^2 * 0.5 * log2(e))
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));
+    const float ax = fabsf(x);
+    const float w = ax * 0.84932180028801904f;                 // sqrt(0.5 * log2(e))
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27273748f, w, 1.0f)));   // p / sqrt(log2(e))
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(w * -w));
     float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
     poly = fmaf(poly, t, 0.5f * 1.421413741f);
     poly = fmaf(poly, t, 0.5f * -0.284496736f);
     poly = fmaf(poly, t, 0.5f * 0.254829592f);
     const float h = poly * t * e;
-    return x * (x >= 0.0f ? 1.0f - h : h);
+    return fmaf(-ax, h, fmaxf(x, 0.0f));
 }
 
 }  // namespace mrd
