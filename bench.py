@@ -419,7 +419,8 @@ def main():
         eng.profile(False)
         # executed work: the token-packed BERT GEMMs run on the live rows only (their plans - and so the
         # library's per-launch FLOP figures - are sized for the dense B*S rows), attention on L_b^2 per sample
-        packed = ("bert.qkv", "bert.attn_out+res", "bert.ffn1+gelu", "bert.ffn2+res")
+        packed = ("bert.qkv", "bert.attn_out+res", "bert.attn_out+res+ln", "bert.ffn1+gelu", "bert.ffn2+res",
+                  "bert.ffn2+res+ln")
         for r in rows:
             r["flops_exec"] = r["flops"] * (live_frac if r["label"] in packed else
                                             live_sq_frac if r["label"] == "bert.attention" else 1.0)

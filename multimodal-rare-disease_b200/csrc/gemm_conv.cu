@@ -1740,7 +1740,7 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
                              (g->p.kc_split && g->p.num_k_total <= 6);
     const bool epi2 = (g_split_epilogue & 1) && chain_bound && !(g->p.kc_split && g->p.num_k_total > 6);
     if (g->pair && g->block_n == 256) {
-        if (epi2) return launch_variant<256, MODE_GENERIC, false, true, false, true>(g, stream, sm_limit);
+        if (epi2 || (g_split_epilogue & 8)) return launch_variant<256, MODE_GENERIC, false, true, false, true>(g, stream, sm_limit);
         return launch_variant<256, MODE_GENERIC, false, false, false, true>(g, stream, sm_limit);
     }
     if (epi2) {
