@@ -796,14 +796,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                         const int ph = (t.h0 >> 1) + pr, pw = (t.w0 >> 1) + pc;
                         if (ph >= p.pool_h || pw >= p.pool_w) continue;
                         __nv_bfloat162 m0 = __floats2bfloat162_rn(0.f, 0.f), m1 = m0, m2 = m0, m3 = m0;
+                        // window positions outside the tile are clamped onto the tile's edge: every pooled pixel of the
+                        // 9 x 5 has at least its centre row / column inside, so a clamped position is a duplicate of
+                        // an in-window element (max is idempotent) and the loop has no thread-dependent branch - with
+                        // per-thread `continue`s the four pooled pixels of a warp diverged and every ld.shared was
+                        // issued up to four times (ncu, r02: 15.5 M extra shared-load wavefronts per launch)
 #pragma unroll
                         for (int dr = -1; dr <= 1; ++dr) {
-                            const int hr = 2 * pr + dr;
-                            if (hr < 0 || hr > 15) continue;
+                            const int hr = min(max(2 * pr + dr, 0), 15);
 #pragma unroll
                             for (int dc = -1; dc <= 1; ++dc) {
-                                const int wc = 2 * pc + dc;
-                                if (wc < 0 || wc > 7) continue;
+                                const int wc = min(max(2 * pc + dc, 0), 7);
                                 const int m = hr * 8 + wc;
                                 const uint4 v = *reinterpret_cast<const uint4*>(tile + m * 128 + ((ch ^ (m & 7)) << 4));
                                 m0 = __hmax2(m0, *reinterpret_cast<const __nv_bfloat162*>(&v.x));
