@@ -1410,11 +1410,15 @@ int plan_conv(GemmLaunch* g, const __nv_bfloat16* X, int N, int H, int W, int Ci
     }
     const long long m_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_img;
     const int bn = pick_block_n(Cout, m_tiles, gemm_num_sms());
+    apply_debug_env();
+    // CTA pairs (cta_group::2) for the tensor-bound 3x3 / strided convolutions of layers 3 and 4 as well: two tiles of
+    // 128 output pixels share each weight block
+    g->pair = (g_pair_gemm && bn == 256 && m_tiles * (Cout / 256) >= 2LL * gemm_num_sms()) ? 1 : 0;
     {
         const uint64_t Kt = static_cast<uint64_t>(Cin) * ksize * ksize;
         uint64_t dims[2] = {Kt, (uint64_t)Cout};
         uint64_t str[1] = {Kt * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(g->pair ? bn / 2 : bn)};
         int rc = encode_tensor_map(&p.b_map, Wt, 2, 2, dims, str, box, 128);
         if (rc) return rc;
     }

@@ -180,6 +180,9 @@ def _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res, seed=0):
     (7, 7, 7, 512, 512, 3, 1, 1, False),      # layer4 conv2 (several images per tile, odd count)
     (3, 7, 7, 512, 2048, 1, 1, 1, True),      # layer4 conv3 + identity
     (1, 32, 64, 64, 64, 3, 1, 0, False),      # non-square
+    (205, 14, 14, 256, 256, 3, 1, 1, False),  # layer3 conv2 at pass size: CTA pairs, odd tile count (315)
+    (333, 7, 7, 512, 512, 3, 1, 1, False),    # layer4 conv2 at pass size: CTA pairs, two column tiles
+    (150, 28, 28, 256, 256, 3, 2, 1, False),  # strided 3x3 on CTA pairs (parity-phase views)
 ])
 def test_conv(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res):
     _conv_case(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res)
