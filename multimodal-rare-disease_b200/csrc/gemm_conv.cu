@@ -186,6 +186,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
             if constexpr (PAIR) mbar_init(bar_smem + 448u + 8u * s, 1);   // leader: the peer's stage s has landed
+            if constexpr (PAIR) mbar_init(bar_smem + 440u, 1);            // leader: the peer's resident weights have landed
             mbar_init(rfull_bar(s), 1);
             // ONE arrival per consumed sub-tile, made by the thread that issues the sub-tile's TMA store, i.e. after
             // every consumer thread has turned the residual into shared-memory stores behind a barrier.  An arrival
@@ -283,14 +284,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // 9 taps are then row-shifted views of that span (UMMA descriptors may start at any 128-byte
         // row of a swizzled region), so every input byte crosses L2->SMEM once instead of 9 times.
         // STEM: the 7 tap-row boxes of a tile land in one stage under one barrier.
-        const int n_fixed = bid % p.n_tiles_n;  // grid is a multiple of n_tiles_n: constant per CTA
+        // grid is a multiple of n_tiles_n: constant per CTA.  PAIR (flat mode, one column tile): each CTA keeps its
+        // HALF of the weight panel's rows resident (b_map's box is BLOCK_N / 2 rows)
+        const int n_fixed = PAIR ? 0 : bid % p.n_tiles_n;
         if (lane == 0) {
             mbar_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes));
             if constexpr (FLAT) {
                 for (int kc = 0; kc < p.kc_per_tap; ++kc)
                     for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d(&p.b_map, bres_bar, b_smem + (kc * 9 + tap) * C::B_STAGE,
-                                    (tap * p.kc_per_tap + kc) * 64, n_fixed * BLOCK_N);
+                        tma_load_2d(&p.b_map, bres_bar, b_smem + (kc * 9 + tap) * B_STAGE,
+                                    (tap * p.kc_per_tap + kc) * 64,
+                                    n_fixed * BLOCK_N + (PAIR ? static_cast<int>(pair_rank) * (BLOCK_N / 2) : 0));
             } else {
                 for (int tap = 0; tap < 7; ++tap)
                     tma_load_2d(&p.b_map, bres_bar, b_smem + tap * C::B_STAGE, tap * C::BLOCK_K, 0);
@@ -315,7 +319,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         };
         if (kPrefetch > 0)
             for (int i = 1; i < kPrefetch; ++i) prefetch_tile(bid + i * nblk);
-        for (int tile = bid; tile < total_tiles; tile += nblk) {
+        for (int pit = 0; pit < my_tiles; ++pit) {
+            const int tile = tile_at(pit);
             const TileCoord t = decode_tile(p, tile);
             if (kPrefetch > 0) prefetch_tile(tile + kPrefetch * nblk);
             if constexpr (FLAT) {
@@ -346,35 +351,61 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
     } else if (warp == 1 && WRES) {
         // ------------------------------------------------------------ MMA issuer, weights-resident modes
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
         int sa = 0;
         uint32_t pa = 0;
-        int it = 0;
         mbar_wait(bres_bar, 0);
-        for (int tile = bid; tile < total_tiles; tile += nblk, ++it) {
+        if (PAIR && pair_rank != 0) {
+            // peer CTA of a pair: forwards "my weight panel / my halo span has landed" to the leader, which issues
+            // the 256 x BLOCK_N x 16 MMAs for both (see the generic-mode issuer)
+            if (lane == 0) mbar_arrive_remote(mapa_shared(bar_smem + 440u, 0));
+            __syncwarp();
+            if constexpr (FLAT) {
+                for (int it = 0; it < my_tiles; ++it)
+                    for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                        mbar_wait(full_bar(sa), pa);
+                        if (lane == 0) mbar_arrive_remote(mapa_shared(bar_smem + 448u + 8u * sa, 0));
+                        __syncwarp();
+                        if (++sa == STAGES) { sa = 0; pa ^= 1u; }
+                    }
+            }
+        } else
+        for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
+            if (PAIR && it == 0) mbar_wait(bar_smem + 440u, 0);   // the peer's half of the weight panel is resident
             mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             if constexpr (FLAT) {
                 for (int kc = 0; kc < p.kc_per_tap; ++kc) {
                     mbar_wait(full_bar(sa), pa);
+                    if constexpr (PAIR) mbar_wait(bar_smem + 448u + 8u * sa, pa);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a0 = a_smem + sa * a_stage_bytes;
-                        const uint32_t b0 = b_smem + kc * 9 * C::B_STAGE;
+                        const uint32_t b0 = b_smem + kc * 9 * B_STAGE;
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const int tap_row = (tap / 3) * p.tw + (tap % 3);  // row shift of this tap's view
                             const uint64_t adesc = make_smem_desc(a0 + tap_row * 128, 0, C::SBO, C::LAYOUT);
-                            const uint64_t bdesc = make_smem_desc(b0 + tap * C::B_STAGE, 0, C::SBO, C::LAYOUT);
+                            const uint64_t bdesc = make_smem_desc(b0 + tap * B_STAGE, 0, C::SBO, C::LAYOUT);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                          (kc | tap | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                if constexpr (PAIR)
+                                    umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                                   (kc | tap | k) != 0 ? 1u : 0u);
+                                else
+                                    umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                              (kc | tap | k) != 0 ? 1u : 0u);
+                            }
                         }
-                        umma_commit(empty_bar(sa));
-                        if (kc == p.kc_per_tap - 1) umma_commit(tfull_bar(acc));
+                        if constexpr (PAIR) {
+                            umma_commit_pair(empty_bar(sa), 3);
+                            if (kc == p.kc_per_tap - 1) umma_commit_pair(tfull_bar(acc), 3);
+                        } else {
+                            umma_commit(empty_bar(sa));
+                            if (kc == p.kc_per_tap - 1) umma_commit(tfull_bar(acc));
+                        }
                     }
                     __syncwarp();
                     if (++sa == STAGES) { sa = 0; pa ^= 1u; }
@@ -1197,7 +1228,6 @@ int plan_gemm_impl(GemmLaunch* g, const __nv_bfloat16* A, long long lda, int M, 
     const int bn = force_bn ? force_bn : pick_block_n(N, p.tiles_w, gemm_num_sms());
     apply_debug_env();
     // at least two tiles per SM: below that the pairing has nothing to amortise
-    if (const char* e = getenv("MRD_DEBUG_FLAGS")) p.debug = atoi(e);
     g->pair = (g_pair_gemm && bn == 256 && static_cast<long long>(p.tiles_w) * (N / 256) >= 2LL * gemm_num_sms()) ? 1 : 0;
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
@@ -1575,6 +1605,16 @@ int plan_conv3x3_flat(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, in
         if (Cout % cand == 0 && bn == 0 &&
             fixed + 2 * a_stage + 9 * (Cin / 64) * cand * 128 <= kSmemLimit)
             bn = cand;
+    // CTA pairs (cta_group::2): when only a 64-wide panel fits a single CTA (N = 64 MMAs run at half rate), two CTAs
+    // keep half of a 128-wide panel each and the pair issues 256 x 128 x 16 MMAs at the full rate.  One column tile
+    // only (the resident panel fixes a CTA's column tile).
+    apply_debug_env();
+    const long long flat_tiles = static_cast<long long>((H + th - 1) / th) * N;
+    if (g_pair_gemm && bn == 64 && Cout == 128 && flat_tiles >= 2LL * gemm_num_sms() &&
+        fixed + 2 * a_stage + 9 * (Cin / 64) * 64 * 128 <= kSmemLimit) {
+        g->pair = 1;
+        bn = 128;
+    }
     if (bn == 0) {
         set_last_error("plan_conv3x3_flat: weight panel of Cin=%d does not fit in shared memory", Cin);
         return -1;
@@ -1612,7 +1652,7 @@ int plan_conv3x3_flat(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, in
         const uint64_t Kt = static_cast<uint64_t>(Cin) * 9;
         uint64_t dims[2] = {Kt, (uint64_t)Cout};
         uint64_t str[1] = {Kt * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(g->pair ? bn / 2 : bn)};
         int rc = encode_tensor_map(&p.b_map, Wt, 2, 2, dims, str, box, 128);
         if (rc) return rc;
     }
@@ -1625,7 +1665,7 @@ int plan_conv3x3_flat(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, in
         p.r_map = p.c_map;
     }
     // pipeline: resident weight panel + as many halo-span stages as fit
-    p.b_res_bytes = 9 * (Cin / 64) * bn * 128;
+    p.b_res_bytes = 9 * (Cin / 64) * (g->pair ? bn / 2 : bn) * 128;   // per CTA
     p.ring = 0;
     int st = (kSmemLimit - fixed - p.b_res_bytes) / a_stage;
     p.stages = st > kMaxStages ? kMaxStages : st;
@@ -1719,6 +1759,7 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     if (g->lnc)
         return g->pair ? launch_variant<256, MODE_GENERIC, false, false, true, true>(g, stream, sm_limit)
                        : launch_variant<256, MODE_GENERIC, false, false, true>(g, stream, sm_limit);
+    if (g->flat3 && g->pair) return launch_variant<128, MODE_FLAT3, false, true, false, true>(g, stream, sm_limit);
     if (g->flat3 && (g_split_epilogue & 2)) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_FLAT3, false, true>(g, stream, sm_limit);

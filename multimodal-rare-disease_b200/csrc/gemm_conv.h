@@ -74,7 +74,6 @@ struct alignas(64) ConvGemmParams {
     // usable): one record per 128-row stripe = [128][8] (mean, M2) partials + arrival / departure counters (zero
     // between launches: the last warp to leave a stripe resets them).
     float2* ln_stats;
-    int debug;   // timing experiments only (MRD_DEBUG_FLAGS): bit 0 = the pair leader does not wait for the peer's stages
 };
 
 struct GemmLaunch {
