@@ -1606,14 +1606,16 @@ int plan_conv3x3_flat(GemmLaunch* g, const __nv_bfloat16* Xpad, int N, int H, in
             fixed + 2 * a_stage + 9 * (Cin / 64) * cand * 128 <= kSmemLimit)
             bn = cand;
     // CTA pairs (cta_group::2): when only a 64-wide panel fits a single CTA (N = 64 MMAs run at half rate), two CTAs
-    // keep half of a 128-wide panel each and the pair issues 256 x 128 x 16 MMAs at the full rate.  One column tile
-    // only (the resident panel fixes a CTA's column tile).
+    // keep half of a 128-wide panel each and the pair issues 256 x 128 x 16 MMAs at the full rate (layer2 conv2:
+    // 4.70 -> 2.2-2.7 ms per 4096 images).  A 64-channel layer gains too (layer1 conv2: 4.4 -> 3.7 ms): a
+    // 256 x 64 x 16 pair instruction takes ~45-58 cycles against 62 for 128 x 64 x 16 on one SM
+    // (tools/exp_pair_rate.cu).  One column tile only (the resident panel fixes a CTA's column tile).
     apply_debug_env();
     const long long flat_tiles = static_cast<long long>((H + th - 1) / th) * N;
-    if (g_pair_gemm && bn == 64 && Cout == 128 && flat_tiles >= 2LL * gemm_num_sms() &&
-        fixed + 2 * a_stage + 9 * (Cin / 64) * 64 * 128 <= kSmemLimit) {
+    if (g_pair_gemm && bn == 64 && (Cout == 128 || Cout == 64) &&
+        flat_tiles >= 2LL * gemm_num_sms() && fixed + 2 * a_stage + 9 * (Cin / 64) * (Cout / 2) * 128 <= kSmemLimit) {
         g->pair = 1;
-        bn = 128;
+        bn = Cout;
     }
     if (bn == 0) {
         set_last_error("plan_conv3x3_flat: weight panel of Cin=%d does not fit in shared memory", Cin);
@@ -1759,7 +1761,9 @@ int launch_gemm(const GemmLaunch* g, cudaStream_t stream, int sm_limit) {
     if (g->lnc)
         return g->pair ? launch_variant<256, MODE_GENERIC, false, false, true, true>(g, stream, sm_limit)
                        : launch_variant<256, MODE_GENERIC, false, false, true>(g, stream, sm_limit);
-    if (g->flat3 && g->pair) return launch_variant<128, MODE_FLAT3, false, true, false, true>(g, stream, sm_limit);
+    if (g->flat3 && g->pair)
+        return g->block_n == 128 ? launch_variant<128, MODE_FLAT3, false, true, false, true>(g, stream, sm_limit)
+                                 : launch_variant<64, MODE_FLAT3, false, true, false, true>(g, stream, sm_limit);
     if (g->flat3 && (g_split_epilogue & 2)) {
         switch (g->block_n) {
             case 64: return launch_variant<64, MODE_FLAT3, false, true>(g, stream, sm_limit);

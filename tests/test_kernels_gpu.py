@@ -196,6 +196,7 @@ def test_conv(lib, cuda, N, H, W, Cin, Cout, k, stride, act, res):
     (70, 28, 28, 64, 64, 1),     # many tiles per CTA (persistence, ring wrap-around)
     (65, 28, 28, 128, 128, 1),   # layer2 conv2 at pass size: CTA pairs (cta_group::2), odd tile count (455)
     (48, 28, 28, 64, 128, 0),    # CTA pairs, one channel chunk, even tile count
+    (11, 56, 56, 64, 64, 1),     # layer1 conv2 on CTA pairs (64-wide tile over the pair), odd tile count (308 + 0)
 ])
 def test_conv3x3_flat(lib, cuda, N, H, W, Cin, Cout, act):
     """1x1 conv writing the interior of a zero-bordered buffer, then the flat-shift 3x3 conv on it."""
