@@ -274,7 +274,7 @@ def main():
     ap.add_argument("--tok-chunk", type=int, default=0)
     ap.add_argument("--cpu-samples", type=int, default=128,
                     help="samples per CPU pass: the reference arm's step, and (x2) the cpu_baseline leg")
-    ap.add_argument("--micro-batch", type=int, default=1024)
+    ap.add_argument("--micro-batch", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default="")

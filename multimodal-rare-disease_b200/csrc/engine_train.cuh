@@ -404,7 +404,7 @@ int run_backbone_train(mrd_ctx* c, const void* images, int img_dtype, int B, int
         return -1;
     }
     TrainState* t = train_state(c);
-    MRD_TRY(ensure_cnn_ws(c, H, W));
+    MRD_TRY(ensure_cnn_ws(c, B, H, W));
     MRD_TRY(train_cnn_pack(c, s));
     MRD_TRY(train_cnn_plan(c, B, H, W));
     TrainCnn* tc = t->cnn;

@@ -308,7 +308,7 @@ class MultimodalClassifier(B200Module):
         return predicted, confidence
 
     def forward_host(self, images: torch.Tensor, input_ids: torch.Tensor,
-                     attention_mask: Optional[torch.Tensor], micro_batch: int = 1024, *,
+                     attention_mask: Optional[torch.Tensor], micro_batch: int = 2048, *,
                      logits_out: Optional[torch.Tensor] = None, next_batch=None) -> Dict[str, torch.Tensor]:
         """forward() for batches that still live in HOST memory (what the reference's callers hold
         before `.to(device)`, src/train.py:252-255 / src/predict.py:220-238).
@@ -316,9 +316,9 @@ class MultimodalClassifier(B200Module):
         The batch is cut into micro-batches; a copy stream moves micro-batch i+1 host->device (pinned
         memory makes the copies asynchronous) while the kernels of micro-batch i run, so the PCIe
         transfer (602 KB per image) hides behind the compute.  Returns device tensors like forward().
-        micro_batch = 1024 by default (two 616 MB staging slots on the device): measured on a B200, 4096 samples per
-        call, 256 / 512 / 1024 rows per micro-batch give 32.9 / 35.3 / 35.9 k samples/s against 36.0 k for inputs
-        that are already resident - small passes lose tiles per SM in every kernel.
+        micro_batch = 2048 by default (two 1.2 GB staging slots on the device): measured on a B200, 4096 samples per
+        call, 256 / 512 / 1024 / 2048 rows per micro-batch give 32.9 / 35.3 / 35.9 / 36.9 k samples/s against
+        36.0 - 37.2 k for inputs that are already resident - small passes lose tiles per SM in every kernel.
 
         next_batch = (images, input_ids, attention_mask) of the NEXT call (what a data loader already holds):
         its first micro-batch is copied while this call's last micro-batch computes, so the next call starts on

@@ -45,7 +45,7 @@ def format_predictions(probs: torch.Tensor, class_names: Optional[Sequence[str]]
 @torch.no_grad()
 def predict_batch_tensors(model, images: torch.Tensor, input_ids: torch.Tensor,
                           attention_mask: Optional[torch.Tensor], class_names: Optional[Sequence[str]] = None,
-                          top_k: int = 3, micro_batch: int = 1024) -> List[Dict]:
+                          top_k: int = 3, micro_batch: int = 2048) -> List[Dict]:
     """Preprocessed tensors (on the host or on the model's device) -> `predict_batch`-style results.
     Host tensors should be pinned for the copies to overlap the kernels."""
     if images.shape[0] != input_ids.shape[0]:
@@ -82,7 +82,7 @@ def load_checkpoint(model, checkpoint_path: Union[str, Path], strict: bool = Tru
 
 @torch.no_grad()
 def collect_predictions(model, loader: Iterable, mode: str = "multimodal", device=None,
-                        micro_batch: int = 1024) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                        micro_batch: int = 2048) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """`Evaluator.collect_predictions` (src/evaluate.py:79-123) on the B200 path: walks a loader of the reference's
     batch dicts ({"image", "input_ids", "attention_mask", "label"}; image_only loaders may yield (image, label)
     tuples) and returns (predictions i64 [N], true_labels i64 [N], probabilities f32 [N,C]) on the host - the three
