@@ -173,6 +173,7 @@ def _config(args, world):
             "global_batch": args.global_batch, "per_gpu_batch": -(-args.global_batch // world),
             "seq_len": SEQ, "image": IMG, "parallelism": f"dp{world}",
             "l2": "per-rank inputs exceed L2 (>= 308 MB vs 126 MB); no flush between steps",
+            # 0 = the engine's defaults: up to 2048 images per ResNet pass, 524288 tokens per BERT pass
             "img_chunk": args.img_chunk, "tok_chunk": args.tok_chunk, "engine_opts": args.engine_opt}
 
 
