@@ -92,3 +92,39 @@ def test_every_fixture_is_covered():
                      "image_sens_b2_160x96",
                      # training-step fixtures: covered by tests/test_train_oracle.py
                      "train_p0_bn_eval_b4_s32", "train_p0_bn_train_b4_s32"}
+
+
+@pytest.mark.parametrize("use_residual", [True, False])
+def test_fused_tail_weight_folding(weights, use_residual):
+    """The algebra tail_fused_kernel relies on (csrc/tail_fused.h, pack_tail_big): image_proj, text_proj and the two
+    length-1 cross attentions collapse into ONE K-concatenated matrix per LayerNorm input,
+        pre_i = [img | txt] . [Wip | P_i2t Wtp]^T + (bip + P_i2t btp + pb_i2t),   P = Wo Wv, pb = Wo bv + bo,
+    (and symmetrically for pre_t), because a softmax over one key is 1 (src/fusion_model.py:138-164).  Checked here
+    in fp32 on the CPU against the oracle's step-by-step fusion, for both settings of FusionConfig.use_residual."""
+    sd = {k: v.float() for k, v in weights["sens"].items() if v.is_floating_point()}
+    p = "fusion.fusion_layer."
+    g = torch.Generator().manual_seed(3)
+    img, txt = torch.randn(7, 512, generator=g), torch.randn(7, 768, generator=g)
+
+    def folded(att, w_att, b_att, w_res, b_res):
+        P = sd[p + att + "output_proj.weight"] @ sd[p + att + "value_proj.weight"]
+        pb = sd[p + att + "output_proj.weight"] @ sd[p + att + "value_proj.bias"] + sd[p + att + "output_proj.bias"]
+        w_a, b = P @ w_att, P @ b_att + pb
+        w_r = w_res if use_residual else torch.zeros_like(w_res)
+        return w_a, w_r, b + (b_res if use_residual else 0)
+
+    wip, bip = sd[p + "image_proj.weight"], sd[p + "image_proj.bias"]
+    wtp, btp = sd[p + "text_proj.weight"], sd[p + "text_proj.bias"]
+    wa_i, wr_i, b_i = folded("image_to_text_attention.", wtp, btp, wip, bip)      # pre_i: attends to the text
+    wa_t, wr_t, b_t = folded("text_to_image_attention.", wip, bip, wtp, btp)      # pre_t: attends to the image
+    w_big = torch.cat([torch.cat([wr_i, wa_i], 1), torch.cat([wa_t, wr_t], 1)], 0)   # [2F][img_in + txt_in]
+    b_big = torch.cat([b_i, b_t])
+    pre = torch.cat([img, txt], 1) @ w_big.t() + b_big
+    F_ = 512
+    ln = torch.nn.functional.layer_norm
+    io = ln(pre[:, :F_], (F_,), sd[p + "layer_norm_image.weight"], sd[p + "layer_norm_image.bias"], 1e-5)
+    to = ln(pre[:, F_:], (F_,), sd[p + "layer_norm_text.weight"], sd[p + "layer_norm_text.bias"], 1e-5)
+    h = torch.relu(torch.cat([io, to], 1) @ sd[p + "fusion.0.weight"].t() + sd[p + "fusion.0.bias"])
+    fused = h @ sd[p + "fusion.3.weight"].t() + sd[p + "fusion.3.bias"]
+    ref, _ = oracle.attention_fusion(sd, img, txt, use_residual=use_residual)
+    assert _rel(fused, ref) <= 1e-5
