@@ -369,3 +369,29 @@ def test_collect_predictions_and_checkpoint_loader(tmp_path):
     mrd_b200.load_checkpoint(Tiny(), tmp_path / "bare.pt")
     with pytest.raises(FileNotFoundError, match="Checkpoint not found"):
         mrd_b200.load_checkpoint(fresh, tmp_path / "missing.pt")
+
+
+def test_pair_tile_schedule_covers_every_tile_once():
+    """The persistent tile schedule of the cta_group::2 kernels (csrc/gemm_conv.cu, `tile_at`), restated: cluster c of P
+    takes pair-tiles j = c + it * P of ceil(stripes / 2) x n_tiles; j = (stripe pair, column tile); the CTA of rank r
+    works on stripe 2 * pair + r.  Every real tile must be produced exactly once, both CTAs of a cluster must run the
+    same number of iterations on the same column tile (they share the weight block), and a tile outside the matrix
+    appears only as the second stripe of the last pair when the stripe count is odd."""
+    for stripes, ntn, P in ((579, 9, 74), (579, 3, 74), (8, 12, 74), (1, 3, 74), (150, 1, 74), (455, 1, 74), (3, 2, 5)):
+        total = stripes * ntn
+        pair_total = (stripes + 1) // 2 * ntn
+        seen = {}
+        for c in range(P):
+            my_tiles = (pair_total - c + P - 1) // P if pair_total > c else 0
+            for it in range(my_tiles):
+                j = c + it * P
+                pm, n = divmod(j, ntn)
+                tiles = [(2 * pm + r) * ntn + n for r in (0, 1)]
+                assert tiles[0] % ntn == tiles[1] % ntn == n
+                assert tiles[0] < total, "the leader's tile is always inside the matrix"
+                for t in tiles:
+                    if t < total:
+                        seen[t] = seen.get(t, 0) + 1
+                    else:
+                        assert stripes % 2 == 1 and t // ntn == stripes, "only the odd stripe count has a phantom stripe"
+        assert sorted(seen) == list(range(total)) and set(seen.values()) == {1}, (stripes, ntn, P)
